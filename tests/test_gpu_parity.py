@@ -1,0 +1,177 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs.  Bar: BED bytes identical, every integer bit-exact, floats equal."""
+import numpy as np
+import pytest
+
+from decodingustools_b200 import synth
+from decodingustools_b200.callable_loci import (CallableLociContext, admit_reads, stitch_intervals)
+from decodingustools_b200.options import CallableOptions
+from decodingustools_b200.soa import ReadColumns
+from tests.helpers import assert_parity, run_oracle
+from tests.test_host_half import states_to_intervals
+from tests.test_oracle_vs_naive import random_reads
+
+pytestmark = pytest.mark.gpu
+
+WREAL = 4095
+REF10 = b"NNACGTACGT"
+
+
+@pytest.fixture(scope="module")
+def ctx_default():
+    c = CallableLociContext(CallableOptions())
+    yield c
+    c.close()
+
+
+def test_known_answers_through_the_device(ctx_default):
+    opt = CallableOptions()
+    four = ReadColumns.from_records([(2, 0, 60, "5M", 30, f"r{i}") for i in range(4)])
+    dele = ReadColumns.from_records([(2, 0, 60, "2M1D2M", 30, f"r{i}") for i in range(4)])
+    two_low = ReadColumns.from_records([(2, 0, 0 if i < 2 else 60, "5M", 30, f"r{i}") for i in range(10)])
+    one_low = ReadColumns.from_records([(2, 0, 0 if i < 1 else 60, "5M", 30, f"r{i}") for i in range(10)])
+    for reads, expect in [(ReadColumns.empty(), b"c1\t0\t2\tREF_N\nc1\t2\t10\tNO_COVERAGE\n"),
+                          (four, b"c1\t0\t2\tREF_N\nc1\t2\t7\tCALLABLE\nc1\t7\t10\tNO_COVERAGE\n"),
+                          (dele, b"c1\t0\t2\tREF_N\nc1\t2\t4\tCALLABLE\nc1\t4\t5\tLOW_COVERAGE\nc1\t5\t7\tCALLABLE\nc1\t7\t10\tNO_COVERAGE\n"),
+                          (two_low, b"c1\t0\t2\tREF_N\nc1\t2\t7\tPOOR_MAPPING_QUALITY\nc1\t7\t10\tNO_COVERAGE\n"),
+                          (one_low, b"c1\t0\t2\tREF_N\nc1\t2\t7\tCALLABLE\nc1\t7\t10\tNO_COVERAGE\n")]:
+        o, _ = assert_parity([("c1", 0, 10, REF10, reads)], opt, ctx_default)
+        assert o.bed() == expect
+
+
+def test_ka5_ka6_quirks_and_depth_cap():
+    e = ReadColumns.empty()
+    o, _ = assert_parity([("a", 0, 3, b"ACG", e), ("z", 1, 0, b"", e), ("b", 2, 2, b"AC", e)], CallableOptions())
+    assert o.bed() == b"a\t0\t3\tNO_COVERAGE\n" * 3 + b"b\t0\t2\tNO_COVERAGE\n"
+    opt = CallableOptions(max_depth=3, min_depth=1)
+    recs = [(0, 0, 60, "5M", 30, f"a{i}") for i in range(5)] + [(1, 0, 60, "5M", 30, f"b{i}") for i in range(2)]
+    o, _ = assert_parity([("c", 0, 6, b"ACGTAC", ReadColumns.from_records(recs))], opt)
+    assert o.bed() == b"c\t0\t1\tCALLABLE\nc\t1\t5\tEXCESSIVE_COVERAGE\nc\t5\t6\tCALLABLE\n"
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_random_micro_contigs(seed):
+    rng = np.random.default_rng(1000 + seed)
+    length = int(rng.integers(1, 60))
+    ref = bytes(rng.choice(list(b"ACGTNnR"), size=length, p=[.2, .2, .2, .2, .1, .05, .05]).tolist())
+    reads = random_reads(rng, length, int(rng.integers(0, 80)))
+    opt = CallableOptions(min_depth=int(rng.integers(0, 5)), max_depth=int(rng.choice([0, 2, 3, 5, 500])),
+                          min_mapping_quality=int(rng.choice([0, 10, 30])), min_base_quality=int(rng.choice([0, 20, 200])),
+                          min_depth_for_low_mapq=int(rng.integers(0, 6)), max_low_mapq=int(rng.choice([0, 1, 9])),
+                          max_low_mapq_fraction=float(rng.choice([-0.5, 0.0, 0.1, 0.25, 0.5, 1.0])))
+    assert_parity([("chrT", int(rng.integers(0, 3)), length, ref, reads)], opt)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_multi_contig_quirks(seed, ctx_default):
+    rng = np.random.default_rng(5000 + seed)
+    contigs = []
+    for tid, name in enumerate(["chr1", "chr2", "chrM", "chrX", "chrUn"]):
+        length = int(rng.choice([0, 1, 5, 17, 40, 5000]))
+        ref = bytes(rng.choice(list(b"ACGTN"), size=length, p=[.22, .22, .22, .22, .12]).tolist())
+        reads = random_reads(rng, max(length, 1), int(rng.integers(0, 200)), max_len=30) if length > 2 else ReadColumns.empty()
+        contigs.append((name, tid, length, ref, reads))
+    if max(c[2] for c in contigs if c[0] != "chrM") == 0:
+        contigs[0] = ("chr1", 0, 5, b"ACGTN", ReadColumns.empty())
+    assert_parity(contigs, CallableOptions(), ctx_default)
+
+
+@pytest.mark.parametrize("length", [1, 2, WREAL - 1, WREAL, WREAL + 1, 2 * WREAL, 2 * WREAL + 1, 3 * WREAL - 1])
+def test_window_edges(length, ctx_default):
+    """Contig lengths and reads placed exactly on window seams."""
+    rng = np.random.default_rng(length)
+    ref = bytes(rng.choice(list(b"ACGTN"), size=length, p=[.24, .24, .24, .24, .04]).tolist())
+    recs = []
+    for seam in (0, WREAL, 2 * WREAL):
+        for d in (-151, -150, -149, -2, -1, 0, 1):
+            p = seam + d
+            if 0 <= p and p + 150 <= length:
+                for k in range(5):
+                    recs.append((p, 0, int(rng.choice([0, 60])), "150M", rng.choice([2, 37], size=150).tolist(), f"s{seam}_{d}_{k}"))
+                recs.append((p, 0, 60, "20S50M10D50M30S", rng.choice([2, 37], size=150).tolist(), f"c{seam}_{d}"))
+    recs.sort(key=lambda r: r[0])
+    assert_parity([("chrE", 0, length, ref, ReadColumns.from_records(recs))], CallableOptions(), ctx_default)
+
+
+def test_synthetic_short_reads_per_base_and_bed(ctx_default):
+    c = synth.synth_short("chr22", 1_500_000, seed=11)
+    opt = CallableOptions()
+    contigs = [(c.name, 0, c.length, c.ref, c.reads)]
+    o, results = assert_parity(contigs, opt, ctx_default)
+    # per-base counters of the same run
+    oc = run_oracle(contigs, opt, debug=True).contigs[0]
+    raw, qc, low, st = ctx_default.debug_per_base(c.length)
+    assert np.array_equal(raw, oc.raw) and np.array_equal(qc, oc.qc) and np.array_equal(low, oc.low)
+    assert np.array_equal(st, oc.state)
+    assert results[0].summed_coverage == int(c.reads.select(admit_reads(c.reads, 500)).ref_len().sum())
+
+
+def test_streamed_batches_equal_single_push(ctx_default):
+    c = synth.synth_short("chr22", 600_000, seed=12)
+    assert_parity([(c.name, 0, c.length, c.ref, c.reads)], CallableOptions(), ctx_default, batch_reads=10_000)
+    assert_parity([(c.name, 0, c.length, c.ref, c.reads)], CallableOptions(), ctx_default, batch_reads=777)
+
+
+def test_long_reads_indel_heavy(ctx_default):
+    c = synth.synth_long("chr1", 600_000, seed=13)
+    assert c.reads.n_cigar > 50 * c.reads.n
+    assert_parity([(c.name, 0, c.length, c.ref, c.reads)], CallableOptions(), ctx_default)
+    assert_parity([(c.name, 0, c.length, c.ref, c.reads)], CallableOptions(), ctx_default, batch_reads=7)
+
+
+def test_deep_coverage_admission_cap():
+    c = synth.synth_short("chrM", 16_569, seed=14, depth=2000.0)
+    y = synth.synth_short("chrY", 120_000, seed=15, depth=2000.0)
+    o, _ = assert_parity([(y.name, 0, y.length, y.ref, y.reads), (c.name, 1, c.length, c.ref, c.reads)], CallableOptions())
+    assert o.contigs[0].n_admitted < y.reads.n // 2            # the cap is active
+    # max_depth 4000: no cap, true 2000x depth in the shared-memory counters
+    assert_parity([(c.name, 0, c.length, c.ref, c.reads)], CallableOptions(max_depth=4000))
+
+
+def test_region_shards_stitch_to_the_whole(ctx_default):
+    c = synth.synth_short("chr22", 500_000, seed=16)
+    opt = CallableOptions()
+    keep = admit_reads(c.reads, opt.pileup_max_depth, 0)
+    reads = c.reads.select(keep)
+    span = reads.max_ref_span()
+    ctx = ctx_default
+    ctx.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=span)
+    ctx.push_reads(reads)
+    whole = ctx.finish_contig()
+    for cuts in ([0, 250_000, c.length], [0, 4095, 4096, 123_457, 400_000, c.length]):
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            end = reads.end()
+            sel = (reads.pos < b) & (end > a - 1)               # halo: the base left of the shard too
+            ctx.begin_contig(0, c.name, c.length, c.ref, c.length, region=(a, b), max_ref_span=span)
+            ctx.push_reads(reads.select(sel))
+            parts.append(ctx.finish_contig())
+        iv = stitch_intervals([p.intervals for p in parts])
+        assert np.array_equal(iv, whole.intervals)
+        assert np.array_equal(sum(p.state_counts for p in parts), whole.state_counts)
+        assert np.array_equal(sum(p.bins.astype(np.uint64) for p in parts), whole.bins.astype(np.uint64))
+        for k in ("n_covered_bases", "summed_coverage", "summed_baseq", "summed_mapq", "quality_bases"):
+            assert sum(getattr(p, k) for p in parts) == getattr(whole, k), k
+
+
+def test_unsorted_input_is_rejected(ctx_default):
+    from decodingustools_b200._lib import ClbError
+    reads = ReadColumns.from_records([(50, 0, 60, "10M", 30), (20, 0, 60, "10M", 30)])
+    ctx_default.begin_contig(0, "c", 100, b"A" * 100, 100)
+    ctx_default.push_reads(reads)
+    with pytest.raises(ClbError):
+        ctx_default.finish_contig()
+
+
+def test_rerun_resident_is_idempotent(ctx_default):
+    c = synth.synth_short("chr22", 400_000, seed=17)
+    opt = CallableOptions()
+    reads = c.reads.select(admit_reads(c.reads, 500, 0))
+    ctx_default.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
+    ctx_default.push_reads(reads)
+    first = ctx_default.finish_contig()
+    for _ in range(3):
+        ms, again = ctx_default.rerun_resident(fetch=True, copy_intervals=True)
+        assert ms > 0
+        assert np.array_equal(again.intervals, first.intervals) and np.array_equal(again.state_counts, first.state_counts)
+        assert again.summed_baseq == first.summed_baseq and np.array_equal(again.bins, first.bins)
