@@ -57,48 +57,68 @@ def load_peak():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, the library behind nvidia-smi's
+    clocks.sm / clocks_event_reasons.* query of B200_PROFILING.md; falls back to nvidia-smi itself)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
-        self.proc = None
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        import threading
+        self.idx, self.period = gpu_index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        import threading
+        if self._h is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
+        if self._thr is not None:
+            self._stop.set(); self._thr.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}
+        try:   # one-shot fallback
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]),
+                    "reasons": [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi after the timed region"}
         except Exception:
-            self.proc.kill(); out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 def make_workload(scale: float, rank: int, device):
     """chr1-size synthetic contig for this rank (seed differs per rank), admission-filtered and packed."""
     from decodingustools_b200 import synth
-    from decodingustools_b200.callable_loci import admit_reads, count_unique_reads
+    from decodingustools_b200.callable_loci import admit_reads, compact_reads, count_unique_reads
     from decodingustools_b200.options import CallableOptions
     opt = CallableOptions()
     length = max(100_000, int(synth.HG38["chr1"] * scale))
@@ -108,7 +128,7 @@ def make_workload(scale: float, rank: int, device):
     t0 = time.time()
     keep = admit_reads(c.reads, opt.pileup_max_depth, 0)
     n_unique = count_unique_reads(c.reads, keep, c.length)
-    reads = c.reads if bool(keep.all()) else c.reads.select(keep)
+    reads = compact_reads(c.reads, keep)
     t_admit = time.time() - t0
     return opt, c, reads, n_unique, {"synth_s": round(t_gen, 2), "host_admission_s": round(t_admit, 2)}
 
@@ -309,7 +329,8 @@ def main():
             # size-independent sanity of the full-size GPU result + exact parity on the sample prefix
             ctx.begin_contig(0, "chr1", sample_bp, c.ref[:sample_bp], sample_bp, max_ref_span=span)
             from decodingustools_b200.callable_loci import admit_reads
-            ctx.push_reads(sub.select(admit_reads(sub, opt.pileup_max_depth, 0)))
+            from decodingustools_b200.callable_loci import compact_reads
+            ctx.push_reads(compact_reads(sub, admit_reads(sub, opt.pileup_max_depth, 0)))
             g = ctx.finish_contig()
             ok = (g.state_counts.tolist() == oc.counts and g.summed_coverage == oc.summed_coverage and g.summed_baseq == oc.summed_baseq
                   and g.summed_mapq == oc.summed_mapq and g.quality_bases == oc.quality_bases)

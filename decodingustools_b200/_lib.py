@@ -53,7 +53,7 @@ SYMBOLS = [
     "clb_abi_version", "clb_device_count", "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream",
     "clb_begin_contig", "clb_reserve", "clb_push_reads", "clb_finish_contig", "clb_rerun_resident",
     "clb_counters_device", "clb_refresh_counters", "clb_allreduce_nccl", "clb_debug_per_base",
-    "clb_admit_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
+    "clb_admit_reads", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
     "clb_bed_writer_close", "clb_stitch_intervals", "clb_bin_geometry",
 ]
 
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.clb_allreduce_nccl.argtypes = [vp, vp]
     L.clb_debug_per_base.argtypes = [vp, vp, vp, vp, vp]
     L.clb_admit_reads.argtypes = [i32, u32, u64, vp, vp, vp, vp, vp]
+    L.clb_compact_reads.argtypes = [C.POINTER(ReadBatch), vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(ReadBatch)]
     L.clb_bed_writer_open.restype = vp
     L.clb_bed_writer_open.argtypes = [C.c_char_p, u32]
     L.clb_bed_writer_add_contig.argtypes = [vp, C.c_char_p, u32, vp, u64, vp, u32, u32, C.POINTER(C.c_int)]

@@ -184,6 +184,28 @@ def admit_reads(reads: ReadColumns, maxcnt: int, tid: int = 0) -> np.ndarray:
     return keep.astype(bool)
 
 
+def compact_reads(reads: ReadColumns, keep: np.ndarray) -> ReadColumns:
+    """Admitted records only, repacked (host packer step; C++ because the payload columns are GB-sized)."""
+    keep8 = np.ascontiguousarray(keep, dtype=np.uint8)
+    n = int(keep8.sum())
+    if n == reads.n:
+        return reads
+    if n == 0:
+        return ReadColumns.empty()
+    src = _lib.ReadBatch(reads.n, reads.n_cigar, reads.n_qual, _ptr(reads.pos), _ptr(reads.flag), _ptr(reads.mapq),
+                         _ptr(reads.cigar_off), _ptr(reads.cigar), _ptr(reads.qual_off), _ptr(reads.qual))
+    pos = np.empty(n, np.int32); flag = np.empty(n, np.uint16); mapq = np.empty(n, np.uint8)
+    coff = np.empty(n + 1, np.uint32); cig = np.empty(max(reads.n_cigar, 1), np.uint32)
+    qoff = np.empty(n + 1, np.uint64); qual = np.empty(max(reads.n_qual, 1), np.uint8)
+    out = _lib.ReadBatch()
+    rc = _lib.lib().clb_compact_reads(C.byref(src), _ptr(keep8), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(coff), _ptr(cig),
+                                      _ptr(qoff), _ptr(qual), C.byref(out))
+    if rc != 0:
+        raise ClbError(rc, "clb_compact_reads failed")
+    name_id = None if reads.name_id is None else reads.name_id[keep8.astype(bool)]
+    return ReadColumns(pos, flag, mapq, coff, cig[: int(out.n_cigar)], qoff, qual[: int(out.n_qual)], name_id)
+
+
 def count_unique_reads(reads: ReadColumns, keep: np.ndarray, length: int) -> int:
     """ContigProfiler.n_reads: distinct QNAMEs among admitted records that appear in >= 1 column
     (contig_profiler.rs:59-62).  Stays on the host."""
@@ -282,7 +304,7 @@ def process_single_contig(ctx: CallableLociContext, reads: ReadColumns, ref, cou
     stats = contig_stats[tid]
     keep = admit_reads(reads, options.pileup_max_depth, tid)
     stats.n_reads = count_unique_reads(reads, keep, stats.length)
-    admitted = reads if bool(keep.all()) else reads.select(keep)
+    admitted = compact_reads(reads, keep)
     ctx.begin_contig(tid, stats.name, stats.length, ref, counter.largest_contig_length, max_ref_span=admitted.max_ref_span())
     if batch_reads and admitted.n > batch_reads:
         ctx.reserve(admitted.n, admitted.n_cigar, admitted.n_qual)

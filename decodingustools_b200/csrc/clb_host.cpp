@@ -51,6 +51,26 @@ extern "C" int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, c
     return CLB_OK;
 }
 
+extern "C" int clb_compact_reads(const clb_read_batch *in, const uint8_t *keep, int32_t *pos, uint16_t *flag, uint8_t *mapq,
+                                 uint32_t *cigar_off, uint32_t *cigar, uint64_t *qual_off, uint8_t *qual, clb_read_batch *out) {
+    if (!in || !keep || !out) return CLB_E_INVALID;
+    uint64_t n = 0, nc = 0, nq = 0;
+    cigar_off[0] = 0; qual_off[0] = 0;
+    for (uint64_t i = 0; i < in->n_reads; i++) {
+        if (!keep[i]) continue;
+        const uint32_t c0 = in->cigar_off[i], c1 = in->cigar_off[i + 1];
+        const uint64_t q0 = in->qual_off[i], q1 = in->qual_off[i + 1];
+        pos[n] = in->pos[i]; flag[n] = in->flag[i]; mapq[n] = in->mapq[i];
+        memcpy(cigar + nc, in->cigar + c0, (size_t)(c1 - c0) * 4); nc += c1 - c0;
+        memcpy(qual + nq, in->qual + q0, (size_t)(q1 - q0)); nq += q1 - q0;
+        n++;
+        cigar_off[n] = (uint32_t)nc; qual_off[n] = nq;
+    }
+    out->n_reads = n; out->n_cigar = nc; out->n_qual = nq;
+    out->pos = pos; out->flag = flag; out->mapq = mapq; out->cigar_off = cigar_off; out->cigar = cigar; out->qual_off = qual_off; out->qual = qual;
+    return CLB_OK;
+}
+
 extern "C" uint64_t clb_stitch_intervals(const clb_interval *const *shards, const uint64_t *n_per_shard, uint32_t n_shards,
                                          clb_interval *out) {
     uint64_t n = 0;

@@ -106,6 +106,13 @@ __device__ __forceinline__ uint32_t bytes_lt(uint32_t x, uint32_t t_low, uint32_
     return ((~x & t_hi) | (~(x ^ t_hi) & ~d)) & H;
 }
 
+// 0xFF in every byte whose bit 7 is set (PRMT sign-replicate mode; __byte_perm() ignores the replicate bit).
+__device__ __forceinline__ uint32_t bytes_from_msb(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 // Difference-array update for one M-like segment (reads with mapq >= min_mapq only); returns the part of
 // the segment inside the window proper (entries >= 1) as a Seg.  rp/qp: reference/query coordinate of
 // the op start; q0: absolute byte offset of the read's qualities; lq: its quality length.
@@ -161,8 +168,8 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint4 d, uint32_t f,
         // bit (8*j + w) set <=> byte j of word w fails, i.e. chunk byte 4*w + j
         uint32_t m = (l0 >> 7) | (l1 >> 6) | (l2 >> 5) | (l3 >> 4);
         cnt -= __popc(m);
-        sum -= __dp4a(v.x & __byte_perm(l0, 0, 0xba98), 0x01010101u, 0u) + __dp4a(v.y & __byte_perm(l1, 0, 0xba98), 0x01010101u, 0u)
-             + __dp4a(v.z & __byte_perm(l2, 0, 0xba98), 0x01010101u, 0u) + __dp4a(v.w & __byte_perm(l3, 0, 0xba98), 0x01010101u, 0u);
+        sum -= __dp4a(v.x & bytes_from_msb(l0), 0x01010101u, 0u) + __dp4a(v.y & bytes_from_msb(l1), 0x01010101u, 0u)
+             + __dp4a(v.z & bytes_from_msb(l2), 0x01010101u, 0u) + __dp4a(v.w & bytes_from_msb(l3), 0x01010101u, 0u);
         const uint32_t e_chunk = d.y + 16u * c - head;    // entry of chunk byte 0 (may "underflow" for c == 0; fixed by + byte)
         while (m) {
             const uint32_t b = __ffs(m) - 1; m &= m - 1;
@@ -554,7 +561,7 @@ __global__ void k_read_end(const int32_t *pos, const uint32_t *cigar_off, const 
         if (read_end) read_end[r] = (uint32_t)pos[r] + span;
     }
     span = __reduce_max_sync(FULL, span);
-    if ((threadIdx.x & 31) == 0 && span) atomicMax(max_span, span);
+    if (max_span && (threadIdx.x & 31) == 0 && span) atomicMax(max_span, span);
 }
 
 // batch append, step 1: validate ordering of the freshly copied (still batch-relative) columns.

@@ -163,6 +163,12 @@ int clb_debug_per_base(clb_ctx *ctx, uint32_t *raw, uint32_t *qc, uint32_t *low,
 int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
                     const uint32_t *cigar_off, const uint32_t *cigar, uint8_t *keep);
 
+/* Drop the records with keep[i] == 0 and repack the columns (what the host packer does after admission).
+ * Output buffers must be at least as large as the inputs; offsets are rebased to start at 0.
+ * out->n_reads / n_cigar / n_qual receive the compacted sizes. */
+int clb_compact_reads(const clb_read_batch *in, const uint8_t *keep, int32_t *pos, uint16_t *flag, uint8_t *mapq,
+                      uint32_t *cigar_off, uint32_t *cigar, uint64_t *qual_off, uint8_t *qual, clb_read_batch *out);
+
 /* BED writer with the reference's cross-contig behaviour (quirks Q1/Q2): callable_profiler.rs:39-87,122-155. */
 typedef struct clb_bed_writer clb_bed_writer;
 clb_bed_writer *clb_bed_writer_open(const char *path /* NULL = in-memory */, uint32_t largest_contig_len);
