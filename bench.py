@@ -273,6 +273,7 @@ def main():
 
     # ---------------- end-to-end leg through the public API with host buffers
     e2e_ms = []
+    r = first
     for i in range(args.e2e_steps):
         keepalive.clear()
         torch.cuda.synchronize()

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcallable_loci_b200.so")
+LIB_PATH = os.environ.get("CLB_LIB") or os.path.join(_HERE, "libcallable_loci_b200.so")
 
 CLB_OK = 0
 ERRORS = {-1: "CLB_E_INVALID", -2: "CLB_E_CUDA", -3: "CLB_E_INPUT", -4: "CLB_E_UNSUPPORTED", -5: "CLB_E_IO"}
@@ -50,7 +50,7 @@ class ContigResult(C.Structure):
 
 # every symbol include/callable_loci_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "clb_abi_version", "clb_device_count", "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream",
+    "clb_abi_version", "clb_device_count", "clb_window_positions", "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream",
     "clb_begin_contig", "clb_reserve", "clb_push_reads", "clb_finish_contig", "clb_rerun_resident",
     "clb_counters_device", "clb_refresh_counters", "clb_allreduce_nccl", "clb_debug_per_base",
     "clb_admit_reads", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
     L.clb_abi_version.restype = C.c_int
     L.clb_device_count.restype = C.c_int
+    L.clb_window_positions.restype = C.c_uint32
     L.clb_create.restype = vp
     L.clb_create.argtypes = [C.c_int, C.POINTER(Options), C.c_char_p, C.c_size_t]
     L.clb_destroy.argtypes = [vp]

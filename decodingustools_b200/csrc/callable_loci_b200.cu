@@ -154,7 +154,8 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
-    k_pileup_classify<<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+    if (ctx->opt.min_base_quality >= 128) k_pileup_classify<true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+    else k_pileup_classify<false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
     if (time_pileup) CU(cudaEventRecord(time_pileup->b, ctx->s_compute));
     ctx->launches += 2;
     CU(cudaGetLastError());
@@ -280,6 +281,8 @@ extern "C" {
 
 int clb_abi_version(void) { return CLB_ABI_VERSION; }
 
+uint32_t clb_window_positions(void) { return (uint32_t)WREAL; }
+
 int clb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -304,10 +307,11 @@ clb_ctx *clb_create(int device, const clb_options *opt, char *err, size_t err_le
     if ((e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return bail("cudaStreamCreate", e); }
     ctx->s_compute = ctx->s_own;
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
-    if ((e = cudaFuncSetAttribute(k_pileup_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) {
+    if ((e = cudaFuncSetAttribute(k_pileup_classify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pileup_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) {
         clb_destroy(ctx); return bail("cudaFuncSetAttribute(smem)", e);
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_classify, NT, SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_classify<false>, NT, SMEM_BYTES);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc((void **)&ctx->d_first_tab, 65536 * 4)) != cudaSuccess) { clb_destroy(ctx); return bail("cudaMalloc", e); }
     k_first_table<<<65536 / 256, 256, 0, ctx->s_compute>>>(ctx->d_first_tab, opt->max_low_mapq_fraction);

@@ -22,17 +22,30 @@ namespace clb {
 
 constexpr int NT = 256;               // threads per CTA
 constexpr int NWARPS = NT / 32;
-constexpr int PPT = 16;               // window entries per thread in the classify phase
+#ifndef CLB_PPT
+#define CLB_PPT 8
+#endif
+#ifndef CLB_MINB
+#define CLB_MINB 4
+#endif
+#ifndef CLB_UNROLL2
+#define CLB_UNROLL2 1
+#endif
+constexpr int PPT = CLB_PPT;          // window entries per thread in the classify phase
 constexpr int WN = NT * PPT;          // entries per window; entry 0 is the halo position (window start - 1)
 constexpr int WREAL = WN - 1;         // reference positions owned by one window
 constexpr int MAXSEG = 2;             // M-like segments a "simple" read may contribute
 constexpr int FAST_OPS = 6;           // CIGAR ops walked lane-serially; longer CIGARs go warp-cooperative
 constexpr int CHUNK_CAP = 352;        // 16-byte quality chunks mapped per warp round
-constexpr int NFIRST = 128;             // low-MAPQ threshold table entries cached in shared memory
+constexpr int NFIRST = 128;           // low-MAPQ threshold table entries cached in shared memory
+#ifndef CLB_KLQ
+#define CLB_KLQ 8
+#endif
+constexpr int KLQ = CLB_KLQ;          // packed-u8 low-BQ arrays per window
+constexpr int BPA = 7;                // 32-read batches per packed array: 7 * 32 = 224 increments max < 256
+constexpr int LQ_SLAB = WN / 4 + 32;   // words per packed array: 16 words of padding on both sides for clamped / straddling chunks
+constexpr int NRCP = 160;             // reciprocal table size (slots per segment)
 constexpr unsigned FULL = 0xffffffffu;
-
-constexpr int A_WORDS = ((WN + WN / 16 + 4) / 4) * 4;              // padded u32 difference arrays
-constexpr int LQ_WORDS = (((WN + 2 * (WN / 16)) / 2 + 4) / 4) * 4; // padded packed-u16 low-BQ counters
 constexpr int STAT_STRIDE = 16;       // one 128-byte line per global counter (u64 units)
 
 enum { ST_REF_N = 0, ST_CALLABLE = 1, ST_NO_COVERAGE = 2, ST_LOW_COVERAGE = 3, ST_EXCESSIVE = 4, ST_POOR_MAPQ = 5 };
@@ -73,10 +86,6 @@ struct KParams {
     uint8_t *dbg_state;
 };
 
-// padded shared-memory indices: 16 consecutive entries per thread -> lane stride 17 words (9 for u16)
-__device__ __forceinline__ uint32_t pidx(uint32_t e) { return e + (e >> 4); }
-__device__ __forceinline__ uint32_t pidx16(uint32_t e) { return e + ((e >> 4) << 1); }
-
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -90,43 +99,48 @@ __device__ __forceinline__ bool op_qry(uint32_t op) { return op == 0 || op == 1 
 
 struct Seg { uint32_t qrel, rrel, len; };
 
-// Per-CTA constants + shared-memory views
+// Per-CTA constants; shared-memory arrays are addressed through 32-bit shared-window addresses
 struct Win {
     long long wb, wend;            // position of entry 0, exclusive end of positions handled
     uint64_t qbase;                // 16-byte aligned byte offset of the window's first candidate quality
     const uint8_t *qual;
-    uint32_t *sA, *sB, *sLQ;
+    uint32_t sA, sB;               // shared addresses of the difference arrays
     uint32_t min_bq, min_mapq, max_low_mapq;
+    bool lq_packed;                // low-BQ counters: KLQ packed-u8 arrays (fast) or one u32 per position
 };
 
-// SWAR: 0x80 in every byte of x that is < T (unsigned), for any T in 0..255.
-__device__ __forceinline__ uint32_t bytes_lt(uint32_t x, uint32_t t_low, uint32_t t_hi) {
-    const uint32_t H = 0x80808080u;
-    uint32_t d = (x | H) - t_low;                        // bit7 = ((x & 0x7f) >= (T & 0x7f)), no cross-byte borrow
-    return ((~x & t_hi) | (~(x ^ t_hi) & ~d)) & H;
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void red_shared(uint32_t saddr, uint32_t val) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(val) : "memory");
+}
+// add only when val != 0: one ISETP + one predicated ATOMS, no branch
+__device__ __forceinline__ void red_shared_nz(uint32_t saddr, uint32_t val) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" :: "r"(saddr), "r"(val) : "memory");
 }
 
-// 0xFF in every byte whose bit 7 is set (PRMT sign-replicate mode; __byte_perm() ignores the replicate bit).
-__device__ __forceinline__ uint32_t bytes_from_msb(uint32_t x) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
-    return r;
+// SWAR: 0x80 in every byte of x that is < T (unsigned).  t_low = (T & 0x7f) * 0x01010101; BQ_HI = (T >= 128).
+template <bool BQ_HI>
+__device__ __forceinline__ uint32_t bytes_lt(uint32_t x, uint32_t t_low) {
+    const uint32_t H = 0x80808080u;
+    const uint32_t d = (x | H) - t_low;                  // bit7 = ((x & 0x7f) >= (T & 0x7f)), no cross-byte borrow
+    return BQ_HI ? (~(x & d) & H) : (~(x | d) & H);
 }
 
 // Difference-array update for one M-like segment (reads with mapq >= min_mapq only); returns the part of
 // the segment inside the window proper (entries >= 1) as a Seg.  rp/qp: reference/query coordinate of
 // the op start; q0: absolute byte offset of the read's qualities; lq: its quality length.
-__device__ __forceinline__ bool emit_m(const Win &W, long long rp, uint32_t qp, uint32_t len, uint64_t q0, uint32_t lq, Seg &out) {
+__device__ __forceinline__ bool emit_m(const Win &W, uint32_t lq_arr, long long rp, uint32_t qp, uint32_t len, uint64_t q0, uint32_t lq, Seg &out) {
     if (qp >= lq) return false;                          // record.qual().get(qpos) == None
     len = min(len, lq - qp);
-    long long s = max(rp, W.wb), e = min(rp + (long long)len, W.wend);
+    const long long s = max(rp, W.wb), e = min(rp + (long long)len, W.wend);
     if (e <= s) return false;
-    uint32_t e0 = (uint32_t)(s - W.wb), e1 = (uint32_t)(e - W.wb);
-    atomicAdd(&W.sB[pidx(e0)], 1u);
-    if (e1 < (uint32_t)WN) atomicAdd(&W.sB[pidx(e1)], 0xffffffffu);
+    uint32_t e0 = (uint32_t)(s - W.wb);
+    const uint32_t e1 = (uint32_t)(e - W.wb);
+    red_shared(W.sB + 4u * e0, 1u);
+    red_shared_nz(W.sB + 4u * min(e1, (uint32_t)WN - 1u), e1 < (uint32_t)WN ? 0xffffffffu : 0u);
     if (e0 == 0) {                                       // covers the halo position: test its one base here
-        uint8_t q = W.qual[q0 + qp + (uint64_t)(W.wb - rp)];
-        if (q < W.min_bq) atomicAdd(&W.sLQ[0], 1u);
+        const uint8_t q = W.qual[q0 + qp + (uint64_t)(W.wb - rp)];
+        red_shared_nz(lq_arr + 64u, q < W.min_bq ? 1u : 0u);   // entry 0 = byte 0 of word 0 in both counter layouts
         e0 = 1;
         if (e1 <= 1) return false;
     }
@@ -138,107 +152,121 @@ __device__ __forceinline__ bool emit_m(const Win &W, long long rp, uint32_t qp, 
 
 // Difference-array update for a whole read (raw depth + low-MAPQ depth packed as lo16|hi16).
 __device__ __forceinline__ void emit_read(const Win &W, long long p, long long end, uint32_t mq, unsigned long long &acc_mapq) {
-    long long s = max(p, W.wb), e = min(end, W.wend);
+    const long long s = max(p, W.wb), e = min(end, W.wend);
     if (e <= s) return;
-    uint32_t e0 = (uint32_t)(s - W.wb), e1 = (uint32_t)(e - W.wb);
-    uint32_t delta = 1u + ((mq <= W.max_low_mapq) ? 0x10000u : 0u);
-    atomicAdd(&W.sA[pidx(e0)], delta);
-    if (e1 < (uint32_t)WN) atomicAdd(&W.sA[pidx(e1)], 0u - delta);
-    uint32_t rs = max(e0, 1u);
+    const uint32_t e0 = (uint32_t)(s - W.wb), e1 = (uint32_t)(e - W.wb);
+    const uint32_t delta = 1u + ((mq <= W.max_low_mapq) ? 0x10000u : 0u);
+    red_shared(W.sA + 4u * e0, delta);
+    red_shared_nz(W.sA + 4u * min(e1, (uint32_t)WN - 1u), e1 < (uint32_t)WN ? 0u - delta : 0u);
+    const uint32_t rs = max(e0, 1u);
     if (mq >= W.min_mapq && e1 > rs) acc_mapq += (unsigned long long)mq * (e1 - rs);
 }
 
-// One 16-byte quality chunk of one segment.
-__device__ __forceinline__ void process_chunk(const Win &W, uint4 d, uint32_t f, uint4 v, const uint4 *sMaskLo, const uint4 *sMaskHi,
-                                              uint32_t t_low, uint32_t t_hi, uint32_t &acc_sum, uint32_t &acc_cnt) {
-    const uint32_t c = f - d.w;
-    const uint32_t head = d.x & 15u;
-    const uint32_t lo = c == 0 ? head : 0u;
-    const uint32_t rem = head + d.z - 16u * c;            // bytes from chunk start to segment end (>= 1)
-    const uint32_t hi = min(16u, rem);
+// One 16-byte quality chunk.  e0 = window entry of chunk byte 0 (may be < 0 or past the window for bytes outside
+// [lo, hi), which are forced to 0xFF so they never fail and are subtracted from the sums).  Straight-line code:
+// shared-memory atomics are cheaper on sm_100a (about one warp-wide ATOMS per clock per SM) than branches around them.
+template <bool BQ_HI>
+__device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int e0, uint32_t lo, uint32_t hi, uint4 v, const uint4 *sMaskLo,
+                                              const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum, uint32_t &acc_cnt) {
     const uint4 ml = sMaskLo[lo], mh = sMaskHi[hi];       // 0xFF in bytes outside [lo, hi)
     v.x |= ml.x | mh.x; v.y |= ml.y | mh.y; v.z |= ml.z | mh.z; v.w |= ml.w | mh.w;
-    const uint32_t l0 = bytes_lt(v.x, t_low, t_hi), l1 = bytes_lt(v.y, t_low, t_hi);
-    const uint32_t l2 = bytes_lt(v.z, t_low, t_hi), l3 = bytes_lt(v.w, t_low, t_hi);
-    uint32_t sum = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+    const uint32_t l0 = bytes_lt<BQ_HI>(v.x, t_low), l1 = bytes_lt<BQ_HI>(v.y, t_low);        // 0x80 in every failing byte
+    const uint32_t l2 = bytes_lt<BQ_HI>(v.z, t_low), l3 = bytes_lt<BQ_HI>(v.w, t_low);
+    const uint32_t ONES = 0x01010101u;
+    // dot products against the 0x80 flags give 128 x (count, sum) of the failing bytes
+    const uint32_t tot = __dp4a(v.x, ONES, __dp4a(v.y, ONES, __dp4a(v.z, ONES, __dp4a(v.w, ONES, 0u))));
+    const uint32_t nf128 = __dp4a(l0, ONES, __dp4a(l1, ONES, __dp4a(l2, ONES, __dp4a(l3, ONES, 0u))));
+    const uint32_t sf128 = __dp4a(v.x, l0, __dp4a(v.y, l1, __dp4a(v.z, l2, __dp4a(v.w, l3, 0u))));
     const uint32_t ninv = lo + (16u - hi);
-    sum -= 255u * ninv;
-    uint32_t cnt = 16u - ninv;
-    if (l0 | l1 | l2 | l3) {
-        // bit (8*j + w) set <=> byte j of word w fails, i.e. chunk byte 4*w + j
-        uint32_t m = (l0 >> 7) | (l1 >> 6) | (l2 >> 5) | (l3 >> 4);
-        cnt -= __popc(m);
-        sum -= __dp4a(v.x & bytes_from_msb(l0), 0x01010101u, 0u) + __dp4a(v.y & bytes_from_msb(l1), 0x01010101u, 0u)
-             + __dp4a(v.z & bytes_from_msb(l2), 0x01010101u, 0u) + __dp4a(v.w & bytes_from_msb(l3), 0x01010101u, 0u);
-        const uint32_t e_chunk = d.y + 16u * c - head;    // entry of chunk byte 0 (may "underflow" for c == 0; fixed by + byte)
+    acc_sum += tot - 255u * ninv - (sf128 >> 7);
+    acc_cnt += 16u - ninv - (nf128 >> 7);
+    const uint32_t f0 = l0 >> 7, f1 = l1 >> 7, f2 = l2 >> 7, f3 = l3 >> 7;                    // 1 in every failing byte
+    if (W.lq_packed) {
+        // four positions per 32-bit word, one byte each: shift the 16 fail flags to the entry alignment and add them
+        // with five unconditional atomics (a byte takes <= 224 increments, see BPA).  Out-of-window chunks carry no
+        // flags; their address is clamped into the array.
+        const int ec = max(-16, min(e0, WN));
+        const uint32_t sh = ((uint32_t)ec & 3u) << 3;
+        const uint32_t base = lq_arr + 64u + (uint32_t)((ec >> 2) * 4);      // arrays start 16 words into their slab
+        red_shared(base + 0, f0 << sh);
+        red_shared(base + 4, __funnelshift_l(f0, f1, sh));
+        red_shared(base + 8, __funnelshift_l(f1, f2, sh));
+        red_shared(base + 12, __funnelshift_l(f2, f3, sh));
+        red_shared(base + 16, __funnelshift_l(f3, 0u, sh));
+    } else {
+        uint32_t m = f0 | (f1 << 1) | (f2 << 2) | (f3 << 3);      // bit (8*j + w) <=> chunk byte 4*w + j
         while (m) {
             const uint32_t b = __ffs(m) - 1; m &= m - 1;
-            const uint32_t e = e_chunk + ((b & 7u) << 2) + (b >> 3);
-            const uint32_t i16 = pidx16(e);
-            atomicAdd(&W.sLQ[i16 >> 1], 1u << ((i16 & 1u) << 4));
+            red_shared(lq_arr + 64u + 4u * (uint32_t)(e0 + (int)(((b & 7u) << 2) + (b >> 3))), 1u);
         }
     }
-    acc_sum += sum; acc_cnt += cnt;
 }
 
-// Warp-collective: stream the qualities of the segments held in the lanes' registers.
-__device__ __forceinline__ void process_segments(const Win &W, int nseg, const Seg (&seg)[MAXSEG], uint4 *myDesc, uint8_t *myMap,
-                                                 const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t t_hi,
-                                                 uint32_t &acc_sum, uint32_t &acc_cnt, int lane) {
-    uint32_t nc[MAXSEG]; uint32_t nch = 0;
-#pragma unroll
-    for (int k = 0; k < MAXSEG; k++) { nc[k] = k < nseg ? (((seg[k].qrel & 15u) + seg[k].len + 15u) >> 4) : 0u; nch += nc[k]; }
-    uint32_t incl = nch;
-#pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(FULL, incl, dd); if (lane >= dd) incl += t; }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;
-    const uint32_t cf = incl - nch;
-    {
-        uint32_t cfk = cf;
-#pragma unroll
-        for (int k = 0; k < MAXSEG; k++) if (k < nseg) { myDesc[k * 32 + lane] = make_uint4(seg[k].qrel, seg[k].rrel, seg[k].len, cfk); cfk += nc[k]; }
-    }
+// Warp-collective: stream the qualities of the n_owner segments whose descriptors (qrel, rrel, len, n_chunks) sit in
+// myDesc[0..n_owner).  Every segment gets S2 slots of two consecutive chunks (S2 = ceil(largest chunk count / 2)), so
+// slot f belongs to segment f / S2: no lookup table and no prefix sum; slots past a segment's end run empty.
+template <bool BQ_HI>
+__device__ __forceinline__ void process_slots(const Win &W, uint32_t lq_arr, uint32_t n_owner, uint32_t S2, const uint4 *myDesc,
+                                              const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
+                                              uint32_t &acc_sum, uint32_t &acc_cnt, int lane) {
+    const uint32_t total = n_owner * S2;
+    const uint32_t rcp = S2 < (uint32_t)NRCP ? sRcp[S2] : 0xffffffffu / S2 + 1u;     // ceil(2^32 / S2): exact quotient for f < 2^32 / S2
     const uint8_t *qb = W.qual + W.qbase;
-    for (uint32_t lo = 0; lo < total; lo += CHUNK_CAP) {
-        const uint32_t hi = min(total, lo + (uint32_t)CHUNK_CAP);
-        uint32_t cfk = cf;
-#pragma unroll
-        for (int k = 0; k < MAXSEG; k++) if (k < nseg) {
-            const uint32_t a = max(cfk, lo), b = min(cfk + nc[k], hi);
-            for (uint32_t c = a; c < b; c++) myMap[c - lo] = (uint8_t)(k * 32 + lane);
-            cfk += nc[k];
-        }
-        __syncwarp();
-        for (uint32_t f = lo + lane; f < hi; f += 64) {
-            const uint32_t f2 = f + 32; const bool has2 = f2 < hi;
-            const uint4 d1 = myDesc[myMap[f - lo]];
-            const uint4 v1 = ldg_stream(reinterpret_cast<const uint4 *>(qb + (d1.x & ~15u)) + (f - d1.w));
-            uint4 d2 = d1, v2 = v1;
-            if (has2) { d2 = myDesc[myMap[f2 - lo]]; v2 = ldg_stream(reinterpret_cast<const uint4 *>(qb + (d2.x & ~15u)) + (f2 - d2.w)); }
-            process_chunk(W, d1, f, v1, sMaskLo, sMaskHi, t_low, t_hi, acc_sum, acc_cnt);
-            if (has2) process_chunk(W, d2, f2, v2, sMaskLo, sMaskHi, t_low, t_hi, acc_sum, acc_cnt);
-        }
-        __syncwarp();
+    for (uint32_t f = lane; f < total; f += 32) {
+        const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
+        const uint32_t c = 2u * (f - o * S2);
+        const uint4 d = myDesc[o];
+        const uint32_t head = d.x & 15u;
+        const int rem = (int)(head + d.z) - (int)(16u * c);            // bytes from chunk c's start to the segment end
+        if (rem <= 0) continue;
+        const uint4 *src = reinterpret_cast<const uint4 *>(qb + (d.x & ~15u)) + c;
+        const uint4 v0 = ldg_stream(src);
+        const uint4 v1 = ldg_stream(src + 1);                             // may lie past the segment (buffers are padded): masked below
+        const int e0 = (int)(d.y + 16u * c) - (int)head;
+        process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
+        process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)max(0, min(rem - 16, 16)), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
     }
 }
 
-constexpr size_t SMEM_BYTES = (size_t)(2 * A_WORDS + LQ_WORDS) * 4 + 2 * 17 * 16 + NFIRST * 4
-                            + (size_t)NWARPS * MAXSEG * 32 * 16 + (size_t)NWARPS * CHUNK_CAP + 64 * 4 + NT + N_STATS * 8 + 16;
+__device__ __forceinline__ uint32_t seg_chunks(const Seg &s) { return ((s.qrel & 15u) + s.len + 15u) >> 4; }
 
-__global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
+// Warp-collective: lanes holding a segment (has) publish it compactly into myDesc and the warp streams them.
+template <bool BQ_HI>
+__device__ __forceinline__ void run_segments(const Win &W, uint32_t lq_arr, bool has, const Seg &sg, uint4 *myDesc, const uint32_t *sRcp,
+                                             const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum, uint32_t &acc_cnt,
+                                             int lane) {
+    const uint32_t bal = __ballot_sync(FULL, has);
+    if (bal == 0) return;
+    const uint32_t nc = has ? seg_chunks(sg) : 0u;
+    const uint32_t S2 = (__reduce_max_sync(FULL, nc) + 1u) >> 1;
+    if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = make_uint4(sg.qrel, sg.rrel, sg.len, nc);
+    __syncwarp();
+    process_slots<BQ_HI>(W, lq_arr, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+    __syncwarp();
+}
+
+// shared memory: A | B | LQ (KLQ packed-u8 arrays) | masks | first | desc | scan | last | warp stats | next
+constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
+constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)NWARPS * 32 * 16 + 64 * 4 + NT
+                            + (size_t)NWARPS * N_STATS * 8 + 16;
+static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
+static_assert(SMEM_COUNTER_WORDS % 4 == 0, "counter region is zeroed with 16-byte stores");
+
+template <bool BQ_HI>
+__global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *sB = sA + A_WORDS;
-    uint32_t *sLQ = sB + A_WORDS;
-    uint4 *sMaskLo = reinterpret_cast<uint4 *>(sLQ + LQ_WORDS);
+    uint32_t *sB = sA + WN;
+    uint32_t *sLQ = sB + WN;
+    uint4 *sMaskLo = reinterpret_cast<uint4 *>(sLQ + LQ_SLAB * KLQ);
     uint4 *sMaskHi = sMaskLo + 17;
     uint32_t *sFirst = reinterpret_cast<uint32_t *>(sMaskHi + 17);
-    uint4 *sDesc = reinterpret_cast<uint4 *>(sFirst + NFIRST);
-    uint8_t *sMap = reinterpret_cast<uint8_t *>(sDesc + NWARPS * MAXSEG * 32);
-    uint32_t *sScan = reinterpret_cast<uint32_t *>(sMap + NWARPS * CHUNK_CAP);
+    uint32_t *sRcp = sFirst + NFIRST;
+    uint4 *sDesc = reinterpret_cast<uint4 *>(sRcp + NRCP);
+    uint32_t *sScan = reinterpret_cast<uint32_t *>(sDesc + NWARPS * 32);
     uint8_t *sLast = reinterpret_cast<uint8_t *>(sScan + 64);
-    unsigned long long *sStats = reinterpret_cast<unsigned long long *>(sLast + NT + ((16 - (NT & 15)) & 15));
+    unsigned long long *sWStats = reinterpret_cast<unsigned long long *>(sLast + NT);
+    uint32_t *sNext = reinterpret_cast<uint32_t *>(sWStats + NWARPS * N_STATS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w = P.win_first + blockIdx.x;
@@ -246,22 +274,28 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
     Win W;
     W.wb = (long long)P.region_start + (long long)w * WREAL - 1;
     W.wend = min(W.wb + WN, (long long)P.region_end);
-    W.qual = P.qual; W.sA = sA; W.sB = sB; W.sLQ = sLQ;
+    W.qual = P.qual; W.sA = smem_addr(sA); W.sB = smem_addr(sB);
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
     const uint32_t r_lo = P.win_rlo[w], r_hi = P.win_rhi[w];
+    const uint32_t n_batches = (r_hi - r_lo + 31u) >> 5;
+    const uint32_t n_lq = (n_batches + BPA - 1) / BPA;     // packed arrays needed
+    W.lq_packed = n_lq <= (uint32_t)KLQ;
     W.qbase = 0;
     if (r_hi > r_lo) {
         W.qbase = P.qual_off[r_lo] & ~15ull;
         if (P.qual_off[r_hi] - W.qbase > 0xfffffff0ull || r_hi - r_lo > 65535u) {
-            // narrow (16-bit) counters and 32-bit quality offsets cannot represent this window
+            // 16-bit depth fields and 32-bit quality offsets cannot represent this window
             if (tid == 0) atomicOr(P.err, (r_hi - r_lo > 65535u) ? ERR_DEPTH : ERR_QUAL_SPAN);
             if (tid == 0) P.win_tab[w] = make_uint2(0, 0);
             return;
         }
     }
 
-    for (int i = tid; i < 2 * A_WORDS + LQ_WORDS; i += NT) sA[i] = 0;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(sA);
+        for (int i = tid; i < (int)(SMEM_COUNTER_WORDS / 4); i += NT) z[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid < 17) {
         uint32_t lo[4], hi[4];
 #pragma unroll
@@ -278,24 +312,29 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
         sMaskHi[tid] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
     if (tid < NFIRST) sFirst[tid] = P.first_tab[tid];
-    if (tid < N_STATS) sStats[tid] = 0;
+    if (tid < NRCP) sRcp[tid] = tid > 1 ? 0xffffffffu / (uint32_t)tid + 1u : 0u;
+    if (tid == 0) *sNext = 0;
     __syncthreads();
 
     // ------------------------------------------------------------------ phase A/B: reads -> counters
-    const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u, t_hi = (P.min_bq & 0x80u) ? 0xffffffffu : 0u;
-    uint4 *myDesc = sDesc + warp * (MAXSEG * 32);
-    uint8_t *myMap = sMap + warp * CHUNK_CAP;
+    const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
+    uint4 *myDesc = sDesc + warp * 32;
+    const uint32_t sLQ_s = smem_addr(sLQ);
     uint32_t acc_sum = 0, acc_cnt = 0;
     unsigned long long acc_mapq = 0;
 
-    for (uint32_t b0 = r_lo + warp * 32; b0 < r_hi; b0 += NWARPS * 32) {
-        const uint32_t r = b0 + lane;
-        Seg seg[MAXSEG]; int nseg = 0;
-        bool cplx = false;
-        int p = 0; uint32_t mq = 0, c0 = 0, c1 = 0, lq = 0; uint64_t q0 = 0;
+    for (;;) {
+        uint32_t bi = 0;
+        if (lane == 0) bi = atomicAdd(sNext, 1u);            // warps pull 32-read batches dynamically
+        bi = __shfl_sync(FULL, bi, 0);
+        if (bi >= n_batches) break;
+        const uint32_t lq_arr = W.lq_packed ? sLQ_s + (bi / BPA) * (uint32_t)(LQ_SLAB * 4) : sLQ_s;
+        const uint32_t r = r_lo + (bi << 5) + lane;
+        int p = 0; uint32_t mq = 0, c0 = 0, nops = 0, lq = 0; uint64_t q0 = 0;
         if (r < r_hi) {
             const uint32_t fl = P.flag[r];
-            c0 = P.cigar_off[r]; c1 = P.cigar_off[r + 1];
+            c0 = P.cigar_off[r];
+            const uint32_t c1 = P.cigar_off[r + 1];
             bool live = !(fl & 4u) && c1 > c0;
             if (live && P.read_end) live = (long long)P.read_end[r] > W.wb;
             if (live) {
@@ -303,57 +342,62 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
                 q0 = P.qual_off[r];
                 const uint64_t ql = P.qual_off[r + 1] - q0;
                 lq = ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql;
-                if (c1 - c0 > (uint32_t)FAST_OPS) cplx = true;
-                else {
-                    uint32_t ops[FAST_OPS]; int nm = 0;
-#pragma unroll
-                    for (int k = 0; k < FAST_OPS; k++) {
-                        ops[k] = (c0 + k < c1) ? P.cigar[c0 + k] : 0xfu;        // op 15, len 0: no effect
-                        nm += op_is_m(ops[k] & 15u) ? 1 : 0;
-                    }
-                    if (nm > MAXSEG) cplx = true;
-                    else {
-                        long long rp = p; uint32_t qp = 0;
-                        const bool pass = mq >= W.min_mapq;
-#pragma unroll
-                        for (int k = 0; k < FAST_OPS; k++) {
-                            const uint32_t op = ops[k] & 15u, len = ops[k] >> 4;
-                            if (op_is_m(op)) {
-                                if (pass && nseg < MAXSEG) { Seg s; if (emit_m(W, rp, qp, len, q0, lq, s)) { seg[nseg < MAXSEG ? nseg : 0] = s; nseg++; } }
-                                rp += len; qp += len;
-                            } else if (op == 2 || op == 3) rp += len;
-                            else if (op == 1 || op == 4) qp += len;
-                        }
-                        emit_read(W, p, rp, mq, acc_mapq);
-                    }
-                }
+                nops = c1 - c0;
             }
         }
-        process_segments(W, nseg, seg, myDesc, myMap, sMaskLo, sMaskHi, t_low, t_hi, acc_sum, acc_cnt, lane);
+        // short CIGARs are walked lane-serially (one loop trip per op, trip count = longest short CIGAR in the warp)
+        bool cplx = nops > (uint32_t)FAST_OPS;
+        const uint32_t nfast = cplx ? 0u : nops;
+        const uint32_t kmax = __reduce_max_sync(FULL, nfast);
+        uint32_t nm = 0;
+        for (uint32_t k = 0; k < kmax; k++) {
+            const uint32_t op = k < nfast ? (P.cigar[c0 + k] & 15u) : 15u;
+            nm += (0x181u >> op) & 1u;                                   // M, =, X
+        }
+        if (nm > (uint32_t)MAXSEG) cplx = true;                          // too many segments for the register slots
+        const bool fast = !cplx && nops > 0;
+        Seg sg0, sg1; bool h0 = false, h1 = false;
+        {
+            long long rp = p; uint32_t qp = 0;
+            const bool pass = mq >= W.min_mapq;
+            for (uint32_t k = 0; k < kmax; k++) {
+                const uint32_t v = (fast && k < nops) ? P.cigar[c0 + k] : 0xfu;
+                const uint32_t op = v & 15u, len = v >> 4;
+                if (((0x181u >> op) & 1u) && pass) {
+                    Seg s;
+                    if (emit_m(W, lq_arr, rp, qp, len, q0, lq, s)) { if (!h0) { sg0 = s; h0 = true; } else { sg1 = s; h1 = true; } }
+                }
+                if ((0x18du >> op) & 1u) rp += len;                      // M, D, N, =, X consume the reference
+                if ((0x193u >> op) & 1u) qp += len;                      // M, I, S, =, X consume the query
+            }
+            if (fast) emit_read(W, p, rp, mq, acc_mapq);
+        }
+        run_segments<BQ_HI>(W, lq_arr, h0, sg0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+        run_segments<BQ_HI>(W, lq_arr, h1, sg1, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
 
         // long CIGARs: the whole warp expands one read at a time with prefix sums over 32 ops
         uint32_t cmask = __ballot_sync(FULL, cplx);
         while (cmask) {
             const int src = __ffs(cmask) - 1; cmask &= cmask - 1;
             const long long cp = __shfl_sync(FULL, p, src);
-            const uint32_t cmq = __shfl_sync(FULL, mq, src), cc0 = __shfl_sync(FULL, c0, src), cc1 = __shfl_sync(FULL, c1, src);
+            const uint32_t cmq = __shfl_sync(FULL, mq, src), cc0 = __shfl_sync(FULL, c0, src), cn = __shfl_sync(FULL, nops, src);
             const uint32_t clq = __shfl_sync(FULL, lq, src);
             const uint64_t cq0 = __shfl_sync(FULL, (unsigned long long)q0, src);
             const bool cpass = cmq >= W.min_mapq;
             long long rp_carry = cp; uint32_t qp_carry = 0;
-            for (uint32_t ob = cc0; ob < cc1; ob += 32) {
-                const uint32_t v = (ob + lane < cc1) ? P.cigar[ob + lane] : 0xfu;
+            for (uint32_t ob = 0; ob < cn; ob += 32) {
+                const uint32_t v = (ob + lane < cn) ? P.cigar[cc0 + ob + lane] : 0xfu;
                 const uint32_t op = v & 15u, len = v >> 4;
-                const uint32_t rl = op_ref(op) ? len : 0u, ql = op_qry(op) ? len : 0u;
+                const uint32_t rl = ((0x18du >> op) & 1u) ? len : 0u, ql = ((0x193u >> op) & 1u) ? len : 0u;
                 uint32_t rs = rl, qs = ql;
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     const uint32_t t1 = __shfl_up_sync(FULL, rs, dd), t2 = __shfl_up_sync(FULL, qs, dd);
                     if (lane >= dd) { rs += t1; qs += t2; }
                 }
-                Seg sg[MAXSEG]; int ns = 0;
-                if (cpass && op_is_m(op)) { Seg s; if (emit_m(W, rp_carry + (long long)(rs - rl), qp_carry + (qs - ql), len, cq0, clq, s)) { sg[0] = s; ns = 1; } }
-                process_segments(W, ns, sg, myDesc, myMap, sMaskLo, sMaskHi, t_low, t_hi, acc_sum, acc_cnt, lane);
+                Seg s; bool hs = false;
+                if (cpass && ((0x181u >> op) & 1u)) hs = emit_m(W, lq_arr, rp_carry + (long long)(rs - rl), qp_carry + (qs - ql), len, cq0, clq, s);
+                run_segments<BQ_HI>(W, lq_arr, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
                 rp_carry += __shfl_sync(FULL, rs, 31); qp_carry += __shfl_sync(FULL, qs, 31);
                 if (rp_carry >= W.wend) break;                           // rest of the read lies right of the window
             }
@@ -364,9 +408,35 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
 
     // ------------------------------------------------------------------ phase C: scan, classify, segment
     const uint32_t ebase = tid * PPT;
-    uint32_t a[PPT], b[PPT];
+    uint32_t a[PPT], b[PPT], lqv[PPT];
+    {
 #pragma unroll
-    for (int k = 0; k < PPT; k++) { a[k] = sA[pidx(ebase + k)]; b[k] = sB[pidx(ebase + k)]; }
+        for (int g = 0; g < PPT / 4; g++) {
+            const uint4 av = *reinterpret_cast<const uint4 *>(sA + ebase + 4 * g), bv = *reinterpret_cast<const uint4 *>(sB + ebase + 4 * g);
+            a[4 * g] = av.x; a[4 * g + 1] = av.y; a[4 * g + 2] = av.z; a[4 * g + 3] = av.w;
+            b[4 * g] = bv.x; b[4 * g + 1] = bv.y; b[4 * g + 2] = bv.z; b[4 * g + 3] = bv.w;
+        }
+        if (W.lq_packed) {
+            uint32_t ev[PPT / 4], od[PPT / 4];                  // 16-bit pair accumulators (4 entries per word)
+#pragma unroll
+            for (int g = 0; g < PPT / 4; g++) { ev[g] = 0; od[g] = 0; }
+            for (uint32_t k = 0; k < n_lq; k++) {
+                const uint32_t *row = sLQ + k * LQ_SLAB + 16 + (ebase >> 2);
+#pragma unroll
+                for (int g = 0; g < PPT / 4; g++) { const uint32_t q = row[g]; ev[g] += q & 0x00ff00ffu; od[g] += (q >> 8) & 0x00ff00ffu; }
+            }
+#pragma unroll
+            for (int g = 0; g < PPT / 4; g++) {
+                lqv[4 * g] = ev[g] & 0xffffu; lqv[4 * g + 1] = od[g] & 0xffffu; lqv[4 * g + 2] = ev[g] >> 16; lqv[4 * g + 3] = od[g] >> 16;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < PPT / 4; g++) {
+                const uint4 qv = *reinterpret_cast<const uint4 *>(sLQ + 16 + ebase + 4 * g);
+                lqv[4 * g] = qv.x; lqv[4 * g + 1] = qv.y; lqv[4 * g + 2] = qv.z; lqv[4 * g + 3] = qv.w;
+            }
+        }
+    }
 #pragma unroll
     for (int k = 1; k < PPT; k++) { a[k] += a[k - 1]; b[k] += b[k - 1]; }
     {
@@ -384,23 +454,21 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
 #pragma unroll
         for (int k = 0; k < PPT; k++) { a[k] += oa; b[k] += ob; }
     }
-    // REF_N bits of this thread's 16 entries
+    // REF_N bits of this thread's entries
     uint32_t nbits;
     {
         const long long p0 = W.wb + (long long)ebase;
         if (p0 >= 0) { const uint32_t wi = (uint32_t)(p0 >> 5); nbits = __funnelshift_r(P.nmask[wi], P.nmask[wi + 1], (uint32_t)(p0 & 31)); }
         else nbits = P.nmask[0] << 1;
     }
-    const uint16_t *sLQ16 = reinterpret_cast<const uint16_t *>(sLQ);
     uint32_t st[PPT];
     uint32_t cnt_pack = 0, covered = 0, sraw = 0, sqc = 0;
     const uint32_t k_first = ebase == 0 ? 1u : 0u;                       // entry 0 is the halo
     const uint32_t k_end = n_ent > ebase ? min((uint32_t)PPT, n_ent - ebase) : 0u;
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        const uint32_t e = ebase + k;
         const uint32_t raw = a[k] & 0xffffu, low = a[k] >> 16;
-        const uint32_t qc = b[k] - sLQ16[pidx16(e)];
+        const uint32_t qc = b[k] - lqv[k];
         const uint32_t fst = raw < (uint32_t)NFIRST ? sFirst[raw] : P.first_tab[raw];
         const bool is_low = raw >= P.min_depth_for_low_mapq && low >= fst;
         uint32_t s;
@@ -416,13 +484,37 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
             cnt_pack += 1u << (5 * s);
             covered += raw > 0 ? 1u : 0u; sraw += raw; sqc += qc;
             if (P.dbg_raw) {
-                const uint32_t o = (uint32_t)(W.wb + e - P.region_start);
+                const uint32_t o = (uint32_t)(W.wb + (long long)(ebase + k) - P.region_start);
                 P.dbg_raw[o] = raw; P.dbg_qc[o] = qc; P.dbg_low[o] = low; P.dbg_state[o] = (uint8_t)s;
             }
         }
     }
     sLast[tid] = (uint8_t)st[PPT - 1];
+    // per-warp partial sums of the additive counters (plain stores, summed after the barrier: no 64-bit smem atomics)
+    {
+        uint32_t v[11];
+#pragma unroll
+        for (int s = 0; s < 6; s++) v[s] = (cnt_pack >> (5 * s)) & 31u;
+        v[6] = covered; v[7] = sraw; v[8] = acc_sum; v[9] = sqc; v[10] = acc_cnt;
+#pragma unroll
+        for (int i = 0; i < 11; i++) v[i] = __reduce_add_sync(FULL, v[i]);
+        unsigned long long mqs = acc_mapq;
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) mqs += __shfl_xor_sync(FULL, mqs, dd);
+        if (lane == 0) {
+            unsigned long long *ws = sWStats + warp * N_STATS;
+#pragma unroll
+            for (int s = 0; s < 6; s++) ws[S_COUNT0 + s] = v[s];
+            ws[S_COVERED] = v[6]; ws[S_SUMCOV] = v[7]; ws[S_SUMBQ] = v[8]; ws[S_QBASES] = v[9]; ws[S_QBASES_B] = v[10]; ws[S_SUMMAPQ] = mqs;
+        }
+    }
     __syncthreads();
+    if (tid < N_STATS) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int j = 0; j < NWARPS; j++) t += sWStats[j * N_STATS + tid];
+        if (t) atomicAdd(&P.stats[tid * STAT_STRIDE], t);
+    }
     // run boundaries
     uint32_t bmask = 0, softmask = 0;
     {
@@ -463,7 +555,7 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
 #pragma unroll
             for (int kk = 0; kk < PPT; kk++) if (kk == k) s = st[kk];
             if (o < P.rec_cap)
-                P.rec[o] = (unsigned long long)(uint32_t)(W.wb + ebase + k) | ((unsigned long long)s << 32)
+                P.rec[o] = (unsigned long long)(uint32_t)(W.wb + (long long)(ebase + k)) | ((unsigned long long)s << 32)
                          | ((unsigned long long)((softmask >> k) & 1u) << 40);
             o++;
         }
@@ -475,7 +567,7 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
         const uint32_t we0 = max(1u, (uint32_t)(warp * 32 * PPT)), we1 = min(n_ent, (uint32_t)((warp + 1) * 32 * PPT));
         if (we1 > we0) {                                                   // warp-uniform
             const uint32_t wbin0 = (uint32_t)(W.wb + we0) / P.stride, wbin1 = (uint32_t)(W.wb + we1 - 1) / P.stride;
-            if (wbin0 == wbin1) {        // whole warp inside one bin (the common case: stride >> 512)
+            if (wbin0 == wbin1) {        // whole warp inside one bin (the common case: stride >> 256)
                 const uint32_t s0 = __reduce_add_sync(FULL, c_call), s1 = __reduce_add_sync(FULL, c_poor), s2 = __reduce_add_sync(FULL, c_refn);
                 if (lane == 0) {
                     if (s0) atomicAdd(&P.bins[wbin0], (unsigned long long)s0);
@@ -502,30 +594,6 @@ __global__ void __launch_bounds__(NT, 4) k_pileup_classify(const KParams P) {
                 }
             }
         }
-    }
-    // per-CTA reduction of the additive counters, then one global atomic per counter
-    {
-        uint32_t v[11];
-#pragma unroll
-        for (int s = 0; s < 6; s++) v[s] = (cnt_pack >> (5 * s)) & 31u;
-        v[6] = covered; v[7] = sraw; v[8] = acc_sum; v[9] = sqc; v[10] = acc_cnt;
-#pragma unroll
-        for (int i = 0; i < 11; i++) v[i] = __reduce_add_sync(FULL, v[i]);
-        unsigned long long mqs = acc_mapq;
-#pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) mqs += __shfl_xor_sync(FULL, mqs, dd);
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < 6; s++) if (v[s]) atomicAdd(&sStats[S_COUNT0 + s], (unsigned long long)v[s]);
-            if (v[6]) atomicAdd(&sStats[S_COVERED], (unsigned long long)v[6]);
-            if (v[7]) atomicAdd(&sStats[S_SUMCOV], (unsigned long long)v[7]);
-            if (v[8]) atomicAdd(&sStats[S_SUMBQ], (unsigned long long)v[8]);
-            if (v[9]) atomicAdd(&sStats[S_QBASES], (unsigned long long)v[9]);
-            if (v[10]) atomicAdd(&sStats[S_QBASES_B], (unsigned long long)v[10]);
-            if (mqs) atomicAdd(&sStats[S_SUMMAPQ], mqs);
-        }
-        __syncthreads();
-        if (tid < N_STATS && sStats[tid]) atomicAdd(&P.stats[tid * STAT_STRIDE], sStats[tid]);
     }
 }
 

@@ -116,6 +116,8 @@ typedef struct clb_ctx clb_ctx;
 /* ---------------------------------------------------------------- device path */
 int         clb_abi_version(void);
 int         clb_device_count(void);
+/* Reference positions owned by one CTA window (region shards are best cut at multiples of it). */
+uint32_t    clb_window_positions(void);
 /* Create a context on `device`.  On failure returns NULL and writes a message to err (if non-NULL). */
 clb_ctx    *clb_create(int device, const clb_options *opt, char *err, size_t err_len);
 void        clb_destroy(clb_ctx *ctx);

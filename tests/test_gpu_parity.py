@@ -13,7 +13,8 @@ from tests.test_oracle_vs_naive import random_reads
 
 pytestmark = pytest.mark.gpu
 
-WREAL = 4095
+from decodingustools_b200 import _lib
+WREAL = int(_lib.lib().clb_window_positions())
 REF10 = b"NNACGTACGT"
 
 
@@ -138,7 +139,7 @@ def test_region_shards_stitch_to_the_whole(ctx_default):
     ctx.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=span)
     ctx.push_reads(reads)
     whole = ctx.finish_contig()
-    for cuts in ([0, 250_000, c.length], [0, 4095, 4096, 123_457, 400_000, c.length]):
+    for cuts in ([0, 250_000, c.length], [0, WREAL, WREAL + 1, 123_457, 400_000, c.length]):
         parts = []
         for a, b in zip(cuts[:-1], cuts[1:]):
             end = reads.end()
