@@ -54,7 +54,7 @@ struct clb_ctx {
     DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end;
     DevBuf nmask, ref_ascii;
     DevBuf stats_padded, counters, rec, win_tab, win_rlo, win_rhi, win_out, intervals, misc;
-    DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state;
+    DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state, timing;
     uint32_t rec_cap = 0;
     bool dbg = false;
 
@@ -137,6 +137,7 @@ KParams make_params(clb_ctx *c) {
     P.rec_cursor = (uint32_t *)c->misc.p + M_CURSOR;
     P.win_tab = (uint2 *)c->win_tab.p;
     P.err = (uint32_t *)c->misc.p + M_ERR;
+    P.timing = (long long *)c->timing.p;
     if (c->dbg) {
         P.dbg_raw = (uint32_t *)c->dbg_raw.p; P.dbg_qc = (uint32_t *)c->dbg_qc.p;
         P.dbg_low = (uint32_t *)c->dbg_low.p; P.dbg_state = (uint8_t *)c->dbg_state.p;
@@ -153,6 +154,11 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
         (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (uint32_t *)ctx->win_rlo.p, (uint32_t *)ctx->win_rhi.p);
     KParams P = make_params(ctx);
     P.win_first = w0;
+    {
+        // typical segment length in 16-byte chunks (+ alignment slack), from the mean quality length of the contig so far
+        const uint64_t mean_q = ctx->n_reads ? ctx->n_qual / ctx->n_reads : 0;
+        P.pool_nc_max = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(4, (mean_q + 30) / 16 + 1));
+    }
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
     if (ctx->opt.min_base_quality >= 128) k_pileup_classify<true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
     else k_pileup_classify<false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
@@ -326,7 +332,7 @@ void clb_destroy(clb_ctx *ctx) {
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end,
                       &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_rlo,
-                      &ctx->win_rhi, &ctx->win_out, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state})
+                      &ctx->win_rhi, &ctx->win_out, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
         release(*b);
     if (ctx->d_first_tab) cudaFree(ctx->d_first_tab);
     if (ctx->h_intervals) cudaFreeHost(ctx->h_intervals);
@@ -573,6 +579,20 @@ int clb_allreduce_nccl(clb_ctx *ctx, void *nccl_comm) {
     const int r = fn(ctx->counters.p, ctx->counters.p, n, ncclUint64, ncclSum, nccl_comm, ctx->s_compute);
     if (r != 0) return fail(ctx, CLB_E_CUDA, "ncclAllReduce returned %d", r);
     CU(cudaStreamSynchronize(ctx->s_compute));
+    return CLB_OK;
+}
+
+/* developer hook (not part of the public header): per-window clock64 stamps of the next runs */
+int clb_debug_timing(clb_ctx *ctx, long long *out, uint32_t max_windows, uint32_t *n_windows) {
+    if (!ctx || !ctx->in_contig || !ctx->finished) return CLB_E_INVALID;
+    int rc;
+    const size_t n = std::min<size_t>(ctx->n_windows, max_windows);
+    if ((rc = ensure(ctx, ctx->timing, (size_t)ctx->n_windows * 64, false, ctx->s_compute))) return rc;
+    rc = run_all_resident(ctx, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy(out, ctx->timing.p, n * 64, cudaMemcpyDeviceToHost));
+    if (n_windows) *n_windows = (uint32_t)n;
+    release(ctx->timing);
     return CLB_OK;
 }
 

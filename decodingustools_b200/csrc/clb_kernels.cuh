@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace clb {
 
@@ -39,7 +40,7 @@ constexpr int FAST_OPS = 6;           // CIGAR ops walked lane-serially; longer 
 constexpr int CHUNK_CAP = 352;        // 16-byte quality chunks mapped per warp round
 constexpr int NFIRST = 128;           // low-MAPQ threshold table entries cached in shared memory
 #ifndef CLB_KLQ
-#define CLB_KLQ 8
+#define CLB_KLQ 6
 #endif
 constexpr int KLQ = CLB_KLQ;          // packed-u8 low-BQ arrays per window
 constexpr int BPA = 7;                // 32-read batches per packed array: 7 * 32 = 224 increments max < 256
@@ -72,6 +73,7 @@ struct KParams {
     // windows
     const uint32_t *win_rlo, *win_rhi;
     uint32_t win_first;
+    uint32_t pool_nc_max;          // segments of at most this many 16-byte chunks go to the CTA-wide pool
     // outputs
     unsigned long long *stats;     // [N_STATS * STAT_STRIDE]
     unsigned long long *bins;      // [3][n_bins]
@@ -84,6 +86,7 @@ struct KParams {
     // optional per-base debug output, indexed by position - region_start
     uint32_t *dbg_raw, *dbg_qc, *dbg_low;
     uint8_t *dbg_state;
+    long long *timing;             // optional (developer builds): 8 clock64 stamps per window
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
@@ -102,6 +105,7 @@ struct Seg { uint32_t qrel, rrel, len; };
 // Per-CTA constants; shared-memory arrays are addressed through 32-bit shared-window addresses
 struct Win {
     long long wb, wend;            // position of entry 0, exclusive end of positions handled
+    uint32_t n_ent;                // entries in use = wend - wb
     uint64_t qbase;                // 16-byte aligned byte offset of the window's first candidate quality
     const uint8_t *qual;
     uint32_t sA, sB;               // shared addresses of the difference arrays
@@ -127,34 +131,34 @@ __device__ __forceinline__ uint32_t bytes_lt(uint32_t x, uint32_t t_low) {
 }
 
 // Difference-array update for one M-like segment (reads with mapq >= min_mapq only); returns the part of
-// the segment inside the window proper (entries >= 1) as a Seg.  rp/qp: reference/query coordinate of
-// the op start; q0: absolute byte offset of the read's qualities; lq: its quality length.
-__device__ __forceinline__ bool emit_m(const Win &W, uint32_t lq_arr, long long rp, uint32_t qp, uint32_t len, uint64_t q0, uint32_t lq, Seg &out) {
-    if (qp >= lq) return false;                          // record.qual().get(qpos) == None
+// the segment inside the window proper (entries >= 1) as a Seg.  rel/qp: window entry (may be negative) and query
+// offset of the op start; q0: absolute byte offset of the read's qualities; lq: its quality length.
+__device__ __forceinline__ bool emit_m(const Win &W, uint32_t lq_arr, int rel, uint32_t qp, uint32_t len, uint64_t q0, uint32_t lq, Seg &out) {
+    if (qp >= lq || rel >= (int)W.n_ent) return false;   // record.qual().get(qpos) == None / right of the window
     len = min(len, lq - qp);
-    const long long s = max(rp, W.wb), e = min(rp + (long long)len, W.wend);
-    if (e <= s) return false;
-    uint32_t e0 = (uint32_t)(s - W.wb);
-    const uint32_t e1 = (uint32_t)(e - W.wb);
+    const uint32_t room = (uint32_t)((int)W.n_ent - rel);                       // > 0
+    const uint32_t e1 = len >= room ? W.n_ent : (uint32_t)(rel + (int)len);     // exclusive end entry, clipped (rel + len may be <= 0)
+    if ((int)e1 <= max(rel, 0)) return false;
+    uint32_t e0 = (uint32_t)max(rel, 0);
     red_shared(W.sB + 4u * e0, 1u);
     red_shared_nz(W.sB + 4u * min(e1, (uint32_t)WN - 1u), e1 < (uint32_t)WN ? 0xffffffffu : 0u);
     if (e0 == 0) {                                       // covers the halo position: test its one base here
-        const uint8_t q = W.qual[q0 + qp + (uint64_t)(W.wb - rp)];
+        const uint8_t q = W.qual[q0 + qp + (uint32_t)(-rel)];
         red_shared_nz(lq_arr + 64u, q < W.min_bq ? 1u : 0u);   // entry 0 = byte 0 of word 0 in both counter layouts
         e0 = 1;
         if (e1 <= 1) return false;
     }
     out.rrel = e0;
     out.len = e1 - e0;
-    out.qrel = (uint32_t)(q0 - W.qbase) + qp + (uint32_t)((W.wb + (long long)e0) - rp);
+    out.qrel = (uint32_t)(q0 - W.qbase) + qp + (uint32_t)((int)e0 - rel);
     return true;
 }
 
-// Difference-array update for a whole read (raw depth + low-MAPQ depth packed as lo16|hi16).
-__device__ __forceinline__ void emit_read(const Win &W, long long p, long long end, uint32_t mq, unsigned long long &acc_mapq) {
-    const long long s = max(p, W.wb), e = min(end, W.wend);
+// Difference-array update for a whole read (raw depth + low-MAPQ depth packed as lo16|hi16).  rel/rel_end: entries.
+__device__ __forceinline__ void emit_read(const Win &W, int rel, int rel_end, uint32_t mq, unsigned long long &acc_mapq) {
+    const int s = max(rel, 0), e = min(rel_end, (int)W.n_ent);
     if (e <= s) return;
-    const uint32_t e0 = (uint32_t)(s - W.wb), e1 = (uint32_t)(e - W.wb);
+    const uint32_t e0 = (uint32_t)s, e1 = (uint32_t)e;
     const uint32_t delta = 1u + ((mq <= W.max_low_mapq) ? 0x10000u : 0u);
     red_shared(W.sA + 4u * e0, delta);
     red_shared_nz(W.sA + 4u * min(e1, (uint32_t)WN - 1u), e1 < (uint32_t)WN ? 0u - delta : 0u);
@@ -202,20 +206,22 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
     }
 }
 
-// Warp-collective: stream the qualities of the n_owner segments whose descriptors (qrel, rrel, len, n_chunks) sit in
-// myDesc[0..n_owner).  Every segment gets S2 slots of two consecutive chunks (S2 = ceil(largest chunk count / 2)), so
-// slot f belongs to segment f / S2: no lookup table and no prefix sum; slots past a segment's end run empty.
+// Stream the qualities of the n_owner segments whose descriptors sit in desc[0..n_owner):
+//   desc = (qrel, rrel, len, n_chunks | low-BQ slab << 16).
+// Every segment gets S2 slots of two consecutive chunks (S2 = ceil(largest chunk count / 2)), so slot f belongs to
+// segment f / S2: no lookup table and no prefix sum; slots past a segment's end run empty.  The caller's threads
+// cover slots f0, f0 + stride, ... (a warp: f0 = lane, stride 32; the whole CTA: f0 = tid, stride NT).
 template <bool BQ_HI>
-__device__ __forceinline__ void process_slots(const Win &W, uint32_t lq_arr, uint32_t n_owner, uint32_t S2, const uint4 *myDesc,
+__device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint4 *desc,
                                               const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
-                                              uint32_t &acc_sum, uint32_t &acc_cnt, int lane) {
+                                              uint32_t &acc_sum, uint32_t &acc_cnt, uint32_t f0, uint32_t stride) {
     const uint32_t total = n_owner * S2;
     const uint32_t rcp = S2 < (uint32_t)NRCP ? sRcp[S2] : 0xffffffffu / S2 + 1u;     // ceil(2^32 / S2): exact quotient for f < 2^32 / S2
     const uint8_t *qb = W.qual + W.qbase;
-    for (uint32_t f = lane; f < total; f += 32) {
+    for (uint32_t f = f0; f < total; f += stride) {
         const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
         const uint32_t c = 2u * (f - o * S2);
-        const uint4 d = myDesc[o];
+        const uint4 d = desc[o];
         const uint32_t head = d.x & 15u;
         const int rem = (int)(head + d.z) - (int)(16u * c);            // bytes from chunk c's start to the segment end
         if (rem <= 0) continue;
@@ -223,6 +229,7 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t lq_arr, uin
         const uint4 v0 = ldg_stream(src);
         const uint4 v1 = ldg_stream(src + 1);                             // may lie past the segment (buffers are padded): masked below
         const int e0 = (int)(d.y + 16u * c) - (int)head;
+        const uint32_t lq_arr = sLQ_s + (d.w >> 16) * (uint32_t)(LQ_SLAB * 4);
         process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
         process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)max(0, min(rem - 16, 16)), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
     }
@@ -230,25 +237,28 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t lq_arr, uin
 
 __device__ __forceinline__ uint32_t seg_chunks(const Seg &s) { return ((s.qrel & 15u) + s.len + 15u) >> 4; }
 
-// Warp-collective: lanes holding a segment (has) publish it compactly into myDesc and the warp streams them.
+// Warp-collective: lanes holding a segment (has) publish it compactly into the warp's descriptor area and stream it
+// right away (segments too long for the CTA pool, and the long-CIGAR path).
 template <bool BQ_HI>
-__device__ __forceinline__ void run_segments(const Win &W, uint32_t lq_arr, bool has, const Seg &sg, uint4 *myDesc, const uint32_t *sRcp,
-                                             const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum, uint32_t &acc_cnt,
-                                             int lane) {
+__device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint32_t slab, bool has, const Seg &sg, uint4 *myDesc,
+                                             const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
+                                             uint32_t &acc_sum, uint32_t &acc_cnt, int lane) {
     const uint32_t bal = __ballot_sync(FULL, has);
     if (bal == 0) return;
     const uint32_t nc = has ? seg_chunks(sg) : 0u;
     const uint32_t S2 = (__reduce_max_sync(FULL, nc) + 1u) >> 1;
-    if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = make_uint4(sg.qrel, sg.rrel, sg.len, nc);
+    if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = make_uint4(sg.qrel, sg.rrel, sg.len, nc | (slab << 16));
     __syncwarp();
-    process_slots<BQ_HI>(W, lq_arr, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+    process_slots<BQ_HI>(W, sLQ_s, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)lane, 32u);
     __syncwarp();
 }
 
 // shared memory: A | B | LQ (KLQ packed-u8 arrays) | masks | first | desc | scan | last | warp stats | next
 constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
-constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)NWARPS * 32 * 16 + 64 * 4 + NT
-                            + (size_t)NWARPS * N_STATS * 8 + 16;
+constexpr int DCAP = 1024;            // CTA-wide segment pool (descriptors); a 32-read batch adds at most 64
+constexpr int BPR = DCAP / 64;        // batches per round
+constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 16 + 64 * 4 + NT
+                            + (size_t)NWARPS * N_STATS * 8 + 32;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
 static_assert(SMEM_COUNTER_WORDS % 4 == 0, "counter region is zeroed with 16-byte stores");
 
@@ -263,13 +273,16 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     uint32_t *sFirst = reinterpret_cast<uint32_t *>(sMaskHi + 17);
     uint32_t *sRcp = sFirst + NFIRST;
     uint4 *sDesc = reinterpret_cast<uint4 *>(sRcp + NRCP);
-    uint32_t *sScan = reinterpret_cast<uint32_t *>(sDesc + NWARPS * 32);
+    uint4 *sPool = sDesc + NWARPS * 32;
+    uint32_t *sScan = reinterpret_cast<uint32_t *>(sPool + DCAP);
     uint8_t *sLast = reinterpret_cast<uint8_t *>(sScan + 64);
     unsigned long long *sWStats = reinterpret_cast<unsigned long long *>(sLast + NT);
-    uint32_t *sNext = reinterpret_cast<uint32_t *>(sWStats + NWARPS * N_STATS);
+    uint32_t *sCtl = reinterpret_cast<uint32_t *>(sWStats + NWARPS * N_STATS);   // [parity][next batch, pool count, pool max chunks]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w = P.win_first + blockIdx.x;
+#define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
+    CLB_STAMP(0);
 
     Win W;
     W.wb = (long long)P.region_start + (long long)w * WREAL - 1;
@@ -277,6 +290,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     W.qual = P.qual; W.sA = smem_addr(sA); W.sB = smem_addr(sB);
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
+    W.n_ent = n_ent;
     const uint32_t r_lo = P.win_rlo[w], r_hi = P.win_rhi[w];
     const uint32_t n_batches = (r_hi - r_lo + 31u) >> 5;
     const uint32_t n_lq = (n_batches + BPA - 1) / BPA;     // packed arrays needed
@@ -313,9 +327,10 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     }
     if (tid < NFIRST) sFirst[tid] = P.first_tab[tid];
     if (tid < NRCP) sRcp[tid] = tid > 1 ? 0xffffffffu / (uint32_t)tid + 1u : 0u;
-    if (tid == 0) *sNext = 0;
+    if (tid < 6) sCtl[tid] = 0;
     __syncthreads();
 
+    CLB_STAMP(1);
     // ------------------------------------------------------------------ phase A/B: reads -> counters
     const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
     uint4 *myDesc = sDesc + warp * 32;
@@ -323,88 +338,142 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     uint32_t acc_sum = 0, acc_cnt = 0;
     unsigned long long acc_mapq = 0;
 
-    for (;;) {
-        uint32_t bi = 0;
-        if (lane == 0) bi = atomicAdd(sNext, 1u);            // warps pull 32-read batches dynamically
-        bi = __shfl_sync(FULL, bi, 0);
-        if (bi >= n_batches) break;
-        const uint32_t lq_arr = W.lq_packed ? sLQ_s + (bi / BPA) * (uint32_t)(LQ_SLAB * 4) : sLQ_s;
-        const uint32_t r = r_lo + (bi << 5) + lane;
-        int p = 0; uint32_t mq = 0, c0 = 0, nops = 0, lq = 0; uint64_t q0 = 0;
-        if (r < r_hi) {
-            const uint32_t fl = P.flag[r];
-            c0 = P.cigar_off[r];
-            const uint32_t c1 = P.cigar_off[r + 1];
-            bool live = !(fl & 4u) && c1 > c0;
-            if (live && P.read_end) live = (long long)P.read_end[r] > W.wb;
-            if (live) {
-                p = P.pos[r]; mq = P.mapq[r];
-                q0 = P.qual_off[r];
-                const uint64_t ql = P.qual_off[r + 1] - q0;
-                lq = ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql;
-                nops = c1 - c0;
+    // Rounds of at most BPR batches of 32 reads: (A) walk the CIGARs, update the difference arrays and append the
+    // M-segments to the CTA-wide pool; (B) after a barrier ALL warps stream the pooled segments slot by slot,
+    // so the quality streaming is balanced across the CTA no matter how the batches fell.
+    const uint32_t n_rounds = (n_batches + BPR - 1) / BPR;
+    const uint32_t bpr = n_rounds ? (n_batches + n_rounds - 1) / n_rounds : 0;
+    for (uint32_t round = 0; round < n_rounds; round++) {
+    uint32_t *ctl = sCtl + 3 * (round & 1);
+    const uint32_t rb1 = min(n_batches, (round + 1) * bpr);
+    // (A) every lane owns up to two candidate reads per trip; the column loads of both are issued before anything
+    //     depends on them, so a window pays two or three DRAM round trips in total instead of per batch.
+    const uint32_t rr0 = r_lo + ((round * bpr) << 5), rr1 = min(r_hi, r_lo + (rb1 << 5));
+    for (uint32_t i0 = rr0 + warp * 32; i0 < rr1; i0 += 2 * NT) {
+        struct RMeta { int rel; uint32_t mq, c0, nops, lq, op0; uint64_t q0; };
+        RMeta M[2];
+        {
+            uint32_t fl[2], c0[2], c1[2], mq[2], re[2]; int ps[2]; uint64_t q0[2], q1[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t r = min(i0 + u * NT + lane, rr1 - 1);     // clamped lanes are discarded below
+                fl[u] = P.flag[r]; c0[u] = P.cigar_off[r]; c1[u] = P.cigar_off[r + 1];
+                ps[u] = P.pos[r]; mq[u] = P.mapq[r]; q0[u] = P.qual_off[r]; q1[u] = P.qual_off[r + 1];
+                re[u] = P.read_end ? P.read_end[r] : 0xffffffffu;
+            }
+            uint32_t op0[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) op0[u] = c1[u] > c0[u] ? P.cigar[c0[u]] : 0xfu;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const bool live = (i0 + u * NT + lane < rr1) && !(fl[u] & 4u) && c1[u] > c0[u] && (long long)re[u] > W.wb;
+                const uint64_t ql = q1[u] - q0[u];
+                M[u].rel = (int)((long long)ps[u] - W.wb); M[u].mq = mq[u]; M[u].c0 = c0[u]; M[u].q0 = q0[u];
+                M[u].lq = ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql;
+                M[u].nops = live ? c1[u] - c0[u] : 0u; M[u].op0 = op0[u];
             }
         }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+        if (i0 + u * NT >= rr1) break;                                   // warp-uniform
+        const uint32_t bi = (i0 + u * NT - r_lo) >> 5;
+        const uint32_t slab = W.lq_packed ? bi / BPA : 0u;
+        const uint32_t lq_arr = sLQ_s + slab * (uint32_t)(LQ_SLAB * 4);
+        const int rel = M[u].rel; const uint32_t mq = M[u].mq, c0 = M[u].c0, nops = M[u].nops, lq = M[u].lq; const uint64_t q0 = M[u].q0;
         // short CIGARs are walked lane-serially (one loop trip per op, trip count = longest short CIGAR in the warp)
         bool cplx = nops > (uint32_t)FAST_OPS;
+        if (__any_sync(FULL, !cplx && nops > 2u)) {                      // <= 2 ops cannot hold more than MAXSEG = 2 segments
+            const uint32_t ncnt = cplx ? 0u : nops;
+            const uint32_t kcnt = __reduce_max_sync(FULL, ncnt);
+            uint32_t nm = 0;
+            for (uint32_t k = 0; k < kcnt; k++) {
+                const uint32_t op = k < ncnt ? (P.cigar[c0 + k] & 15u) : 15u;
+                nm += (0x181u >> op) & 1u;                               // M, =, X
+            }
+            if (nm > (uint32_t)MAXSEG) cplx = true;                      // too many segments for the register slots
+        }
         const uint32_t nfast = cplx ? 0u : nops;
         const uint32_t kmax = __reduce_max_sync(FULL, nfast);
-        uint32_t nm = 0;
-        for (uint32_t k = 0; k < kmax; k++) {
-            const uint32_t op = k < nfast ? (P.cigar[c0 + k] & 15u) : 15u;
-            nm += (0x181u >> op) & 1u;                                   // M, =, X
-        }
-        if (nm > (uint32_t)MAXSEG) cplx = true;                          // too many segments for the register slots
-        const bool fast = !cplx && nops > 0;
         Seg sg0, sg1; bool h0 = false, h1 = false;
         {
-            long long rp = p; uint32_t qp = 0;
+            int rp = rel; uint32_t qp = 0;
             const bool pass = mq >= W.min_mapq;
             for (uint32_t k = 0; k < kmax; k++) {
-                const uint32_t v = (fast && k < nops) ? P.cigar[c0 + k] : 0xfu;
+                const uint32_t v = k < nfast ? (k == 0 ? M[u].op0 : P.cigar[c0 + k]) : 0xfu;  // op 15, len 0: no effect
                 const uint32_t op = v & 15u, len = v >> 4;
                 if (((0x181u >> op) & 1u) && pass) {
                     Seg s;
                     if (emit_m(W, lq_arr, rp, qp, len, q0, lq, s)) { if (!h0) { sg0 = s; h0 = true; } else { sg1 = s; h1 = true; } }
                 }
-                if ((0x18du >> op) & 1u) rp += len;                      // M, D, N, =, X consume the reference
-                if ((0x193u >> op) & 1u) qp += len;                      // M, I, S, =, X consume the query
+                if (((0x18du >> op) & 1u) && rp < (int)WN) rp += (int)len;   // M, D, N, =, X consume the reference (saturates right of the window)
+                if ((0x193u >> op) & 1u) qp += len;                          // M, I, S, =, X consume the query
             }
-            if (fast) emit_read(W, p, rp, mq, acc_mapq);
+            if (nfast) emit_read(W, rel, rp, mq, acc_mapq);
         }
-        run_segments<BQ_HI>(W, lq_arr, h0, sg0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
-        run_segments<BQ_HI>(W, lq_arr, h1, sg1, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+        {
+            // pool append (warp-aggregated); segments longer than the pool's slot budget are streamed by this warp right away
+            const uint32_t nc0 = h0 ? seg_chunks(sg0) : 0u, nc1 = h1 ? seg_chunks(sg1) : 0u;
+            const bool p0 = h0 && nc0 <= P.pool_nc_max, p1 = h1 && nc1 <= P.pool_nc_max;
+            const uint32_t bal0 = __ballot_sync(FULL, p0), bal1 = __ballot_sync(FULL, p1);
+            const uint32_t n0 = __popc(bal0), n1 = __popc(bal1);
+            if (n0 + n1) {
+                const uint32_t mx = __reduce_max_sync(FULL, max(p0 ? nc0 : 0u, p1 ? nc1 : 0u));
+                uint32_t base = 0;
+                if (lane == 0) { base = atomicAdd(&ctl[1], n0 + n1); atomicMax(&ctl[2], mx); }
+                base = __shfl_sync(FULL, base, 0);
+                const uint32_t lt = (1u << lane) - 1u;
+                if (p0) sPool[base + __popc(bal0 & lt)] = make_uint4(sg0.qrel, sg0.rrel, sg0.len, nc0 | (slab << 16));
+                if (p1) sPool[base + n0 + __popc(bal1 & lt)] = make_uint4(sg1.qrel, sg1.rrel, sg1.len, nc1 | (slab << 16));
+            }
+            run_segments<BQ_HI>(W, sLQ_s, slab, h0 && !p0, sg0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+            run_segments<BQ_HI>(W, sLQ_s, slab, h1 && !p1, sg1, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+        }
 
         // long CIGARs: the whole warp expands one read at a time with prefix sums over 32 ops
         uint32_t cmask = __ballot_sync(FULL, cplx);
         while (cmask) {
             const int src = __ffs(cmask) - 1; cmask &= cmask - 1;
-            const long long cp = __shfl_sync(FULL, p, src);
+            const int crel = __shfl_sync(FULL, rel, src);
             const uint32_t cmq = __shfl_sync(FULL, mq, src), cc0 = __shfl_sync(FULL, c0, src), cn = __shfl_sync(FULL, nops, src);
             const uint32_t clq = __shfl_sync(FULL, lq, src);
             const uint64_t cq0 = __shfl_sync(FULL, (unsigned long long)q0, src);
             const bool cpass = cmq >= W.min_mapq;
-            long long rp_carry = cp; uint32_t qp_carry = 0;
+            int rp_carry = crel; uint32_t qp_carry = 0;
             for (uint32_t ob = 0; ob < cn; ob += 32) {
                 const uint32_t v = (ob + lane < cn) ? P.cigar[cc0 + ob + lane] : 0xfu;
                 const uint32_t op = v & 15u, len = v >> 4;
                 const uint32_t rl = ((0x18du >> op) & 1u) ? len : 0u, ql = ((0x193u >> op) & 1u) ? len : 0u;
-                uint32_t rs = rl, qs = ql;
+                unsigned long long rs = rl; uint32_t qs = ql;             // 32 ops of < 2^28 bases each: the reference sum needs 33 bits
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
-                    const uint32_t t1 = __shfl_up_sync(FULL, rs, dd), t2 = __shfl_up_sync(FULL, qs, dd);
+                    const unsigned long long t1 = __shfl_up_sync(FULL, rs, dd); const uint32_t t2 = __shfl_up_sync(FULL, qs, dd);
                     if (lane >= dd) { rs += t1; qs += t2; }
                 }
                 Seg s; bool hs = false;
-                if (cpass && ((0x181u >> op) & 1u)) hs = emit_m(W, lq_arr, rp_carry + (long long)(rs - rl), qp_carry + (qs - ql), len, cq0, clq, s);
-                run_segments<BQ_HI>(W, lq_arr, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
-                rp_carry += __shfl_sync(FULL, rs, 31); qp_carry += __shfl_sync(FULL, qs, 31);
-                if (rp_carry >= W.wend) break;                           // rest of the read lies right of the window
+                const long long my_rel = (long long)rp_carry + (long long)(rs - rl);
+                if (cpass && ((0x181u >> op) & 1u) && my_rel < (long long)WN)
+                    hs = emit_m(W, lq_arr, (int)my_rel, qp_carry + (qs - ql), len, cq0, clq, s);
+                run_segments<BQ_HI>(W, sLQ_s, slab, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+                const long long nxt = (long long)rp_carry + (long long)__shfl_sync(FULL, rs, 31);
+                rp_carry = (int)min(nxt, (long long)WN);                  // saturate right of the window
+                qp_carry += __shfl_sync(FULL, qs, 31);
+                if (rp_carry >= (int)n_ent) break;                       // rest of the read lies right of the window
             }
-            if (lane == 0) emit_read(W, cp, rp_carry, cmq, acc_mapq);
+            if (lane == 0) emit_read(W, crel, rp_carry, cmq, acc_mapq);
+        }
         }
     }
-    __syncthreads();
+    __syncthreads();                                         // pool of this round is complete
+    if (round == 0) CLB_STAMP(2);
+    {
+        const uint32_t pool_n = ctl[1], pool_s2 = (ctl[2] + 1u) >> 1;
+        if (tid < 3) sCtl[3 * ((round + 1) & 1) + tid] = tid == 0 ? rb1 : 0u;     // next round's controls (nobody reads them before the barrier below)
+        process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT);
+    }
+    __syncthreads();                                         // counters final / pool free for the next round
+    }
+    if (n_rounds == 0) __syncthreads();
+    CLB_STAMP(3);
 
     // ------------------------------------------------------------------ phase C: scan, classify, segment
     const uint32_t ebase = tid * PPT;
@@ -450,7 +519,8 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         if (lane == 31) { sScan[warp] = ia; sScan[NWARPS + warp] = ib; }
         __syncthreads();
         uint32_t oa = ia - ta, ob = ib - tb;
-        for (int j = 0; j < warp; j++) { oa += sScan[j]; ob += sScan[NWARPS + j]; }
+#pragma unroll
+        for (int j = 0; j < NWARPS - 1; j++) { if (j < warp) { oa += sScan[j]; ob += sScan[NWARPS + j]; } }
 #pragma unroll
         for (int k = 0; k < PPT; k++) { a[k] += oa; b[k] += ob; }
     }
@@ -461,35 +531,41 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         if (p0 >= 0) { const uint32_t wi = (uint32_t)(p0 >> 5); nbits = __funnelshift_r(P.nmask[wi], P.nmask[wi + 1], (uint32_t)(p0 & 31)); }
         else nbits = P.nmask[0] << 1;
     }
-    uint32_t st[PPT];
-    uint32_t cnt_pack = 0, covered = 0, sraw = 0, sqc = 0;
     const uint32_t k_first = ebase == 0 ? 1u : 0u;                       // entry 0 is the halo
     const uint32_t k_end = n_ent > ebase ? min((uint32_t)PPT, n_ent - ebase) : 0u;
+    const uint32_t vmask = k_end > k_first ? (((1u << k_end) - 1u) & ~((1u << k_first) - 1u)) : 0u;   // entries this thread reports
+    using stp_t = typename std::conditional<(PPT > 8), unsigned long long, uint32_t>::type;
+    stp_t stp = 0;                                                         // 4 bits of state per entry
+    uint32_t cnt_pack = 0, covered = 0, sraw = 0, sqc = 0;
+    const uint32_t min_dflm = P.min_depth_for_low_mapq, min_depth = P.min_depth;
+    const uint32_t max_depth = P.max_depth ? P.max_depth : 0xffffffffu;   // max_depth == 0 disables EXCESSIVE_COVERAGE
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
         const uint32_t raw = a[k] & 0xffffu, low = a[k] >> 16;
         const uint32_t qc = b[k] - lqv[k];
-        const uint32_t fst = raw < (uint32_t)NFIRST ? sFirst[raw] : P.first_tab[raw];
-        const bool is_low = raw >= P.min_depth_for_low_mapq && low >= fst;
-        uint32_t s;
-        if ((nbits >> k) & 1u) s = ST_REF_N;
-        else if (raw == 0) s = ST_NO_COVERAGE;
-        else if (is_low) s = ST_POOR_MAPQ;
-        else if (qc < P.min_depth) s = ST_LOW_COVERAGE;
-        else if (P.max_depth > 0 && qc > P.max_depth) s = ST_EXCESSIVE;
-        else s = ST_CALLABLE;
-        st[k] = s;
-        const bool valid = (uint32_t)k >= k_first && (uint32_t)k < k_end;
-        if (valid) {
-            cnt_pack += 1u << (5 * s);
-            covered += raw > 0 ? 1u : 0u; sraw += raw; sqc += qc;
-            if (P.dbg_raw) {
-                const uint32_t o = (uint32_t)(W.wb + (long long)(ebase + k) - P.region_start);
-                P.dbg_raw[o] = raw; P.dbg_qc[o] = qc; P.dbg_low[o] = low; P.dbg_state[o] = (uint8_t)s;
-            }
+        uint32_t fst = sFirst[min(raw, (uint32_t)NFIRST - 1u)];
+        if (raw >= (uint32_t)NFIRST) fst = P.first_tab[raw];              // deep positions only
+        const bool is_low = raw >= min_dflm && low >= fst;
+        uint32_t s = qc > max_depth ? ST_EXCESSIVE : ST_CALLABLE;
+        s = qc < min_depth ? ST_LOW_COVERAGE : s;
+        s = is_low ? ST_POOR_MAPQ : s;
+        s = raw == 0 ? ST_NO_COVERAGE : s;
+        s = ((nbits >> k) & 1u) ? ST_REF_N : s;
+        stp |= (stp_t)s << (4 * k);
+        const uint32_t valid = (vmask >> k) & 1u;
+        cnt_pack += valid << (5 * s);
+        covered += (raw > 0 ? 1u : 0u) & valid;
+        sraw += valid ? raw : 0u; sqc += valid ? qc : 0u;
+        b[k] = qc;                                                        // keep qc for the optional debug dump
+    }
+    if (P.dbg_raw) {
+#pragma unroll
+        for (int k = 0; k < PPT; k++) if ((vmask >> k) & 1u) {
+            const uint32_t o = (uint32_t)(W.wb + (long long)(ebase + k) - P.region_start);
+            P.dbg_raw[o] = a[k] & 0xffffu; P.dbg_qc[o] = b[k]; P.dbg_low[o] = a[k] >> 16; P.dbg_state[o] = (uint8_t)((uint32_t)(stp >> (4 * k)) & 15u);
         }
     }
-    sLast[tid] = (uint8_t)st[PPT - 1];
+    sLast[tid] = (uint8_t)((uint32_t)(stp >> (4 * (PPT - 1))) & 15u);
     // per-warp partial sums of the additive counters (plain stores, summed after the barrier: no 64-bit smem atomics)
     {
         uint32_t v[11];
@@ -515,21 +591,23 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         for (int j = 0; j < NWARPS; j++) t += sWStats[j * N_STATS + tid];
         if (t) atomicAdd(&P.stats[tid * STAT_STRIDE], t);
     }
-    // run boundaries
-    uint32_t bmask = 0, softmask = 0;
+    CLB_STAMP(4);
+    // run boundaries: entry e starts a run iff its state differs from entry e-1 (the halo for e == 1); the first position
+    // of the region always does (soft when it merely continues the previous shard's run)
+    uint32_t bmask, softmask = 0;
     {
-        uint32_t prev = tid > 0 ? sLast[tid - 1] : 0xffu;
+        const uint32_t prev_last = tid > 0 ? sLast[tid - 1] : 0xfu;
+        const stp_t shifted = (stp << 4) | (stp_t)prev_last;              // state of entry k-1 in nibble k
+        stp_t diff = stp ^ shifted;                                        // non-zero nibble <=> boundary
+        diff |= diff >> 1; diff |= diff >> 2;                              // bit 4k collects the nibble
+        bmask = 0;
 #pragma unroll
-        for (int k = 0; k < PPT; k++) {
-            const bool valid = (uint32_t)k >= k_first && (uint32_t)k < k_end;
-            const long long pp = W.wb + (long long)(ebase + k);
-            const bool forced = pp == 0 || pp == (long long)P.region_start;
-            if (valid && (forced || st[k] != prev)) {
-                bmask |= 1u << k;
-                if (forced && pp != 0 && st[k] == prev) softmask |= 1u << k;
-            }
-            prev = st[k];
+        for (int k = 0; k < PPT; k++) bmask |= ((uint32_t)(diff >> (4 * k)) & 1u) << k;
+        if (w == 0 && tid == 0) {                                          // entry 1 of window 0 is the region's first position
+            if (!(bmask & 2u) && P.region_start != 0) softmask = 2u;
+            bmask |= 2u;
         }
+        bmask &= vmask;
     }
     {
         const uint32_t nb = __popc(bmask);
@@ -539,6 +617,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         if (lane == 31) sScan[16 + warp] = inb;
         __syncthreads();
         uint32_t off = inb - nb, total = 0;
+#pragma unroll
         for (int j = 0; j < NWARPS; j++) { const uint32_t t = sScan[16 + j]; if (j < warp) off += t; total += t; }
         if (tid == 0) {
             const uint32_t base = total ? atomicAdd(P.rec_cursor, total) : 0u;
@@ -551,15 +630,14 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         uint32_t m = bmask;
         while (m) {
             const int k = __ffs(m) - 1; m &= m - 1;
-            uint32_t s = 0;
-#pragma unroll
-            for (int kk = 0; kk < PPT; kk++) if (kk == k) s = st[kk];
+            const uint32_t s = (uint32_t)(stp >> (4 * k)) & 15u;
             if (o < P.rec_cap)
                 P.rec[o] = (unsigned long long)(uint32_t)(W.wb + (long long)(ebase + k)) | ((unsigned long long)s << 32)
                          | ((unsigned long long)((softmask >> k) & 1u) << 40);
             o++;
         }
     }
+    CLB_STAMP(5);
     // bins: positions of CALLABLE / POOR_MAPPING_QUALITY / REF_N per stride-sized bin
     if (P.n_bins) {
         const bool any = k_end > k_first;
@@ -585,7 +663,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
                     for (int k = 0; k < PPT; k++) {
                         if ((uint32_t)k >= k_first && (uint32_t)k < k_end) {
                             const uint32_t bi = (uint32_t)(W.wb + ebase + k) / P.stride;
-                            const uint32_t s = st[k];
+                            const uint32_t s = (uint32_t)(stp >> (4 * k)) & 15u;
                             if (s == ST_CALLABLE) atomicAdd(&P.bins[bi], 1ull);
                             else if (s == ST_POOR_MAPQ) atomicAdd(&P.bins[P.n_bins + bi], 1ull);
                             else if (s == ST_REF_N) atomicAdd(&P.bins[2 * P.n_bins + bi], 1ull);
@@ -595,6 +673,9 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
             }
         }
     }
+    CLB_STAMP(6);
+    if (P.timing && tid == 0) { P.timing[(size_t)w * 8 + 7] = (long long)(r_hi - r_lo); }
+#undef CLB_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ text = open("decodingustools_b200/csrc/clb_kernels.cuh").read().splitlines()
 marks = []
 for i, l in enumerate(text, 1):
     for name, pat in [("bytes_lt", "uint32_t bytes_lt("), ("emit_m", "bool emit_m("), ("emit_read", "void emit_read("), ("process_chunk", "void process_chunk("),
-                      ("process_segments", "void process_segments("), ("kernel_setup", "k_pileup_classify(const KParams P)"), ("phaseA", "phase A/B: reads -> counters"),
+                      ("process_slots", "void process_slots("), ("run_segments", "void run_segments("), ("red_helpers", "uint32_t smem_addr("), ("kernel_setup", "k_pileup_classify(const KParams P)"), ("phaseA", "phase A/B: reads -> counters"),
                       ("complex_path", "long CIGARs: the whole warp"), ("phaseC_scan", "phase C: scan, classify"), ("classify", "uint32_t st[PPT];"),
                       ("boundaries", "// run boundaries"), ("bins", "// bins: positions of"), ("stats", "// per-CTA reduction of the additive"), ("helpers", "// Small helper kernels")]:
         if pat in l: marks.append((i, name))
