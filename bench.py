@@ -61,7 +61,7 @@ class ClockSampler:
     clocks.sm / clocks_event_reasons.* query of B200_PROFILING.md; falls back to nvidia-smi itself)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.02):
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
         import threading
         self.idx, self.period = gpu_index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -301,6 +301,9 @@ def main():
         ms_per_step = total_ms / args.steps
         value = cells_all / (ms_per_step * 1e-3) / 1e9
         achieved = alg_bytes / (pileup_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE resident launch on the default workload, from the ncu --set full
+        # capture summarised in profiles/r01_k_pileup_classify_resident_chr1.txt (same seed, same launch)
+        traffic = 8_416_805_000 if (args.scale == 1.0 and world == 1) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -310,7 +313,7 @@ def main():
                        "l2_policy": f"inputs ({alg_bytes / 1e9:.2f} GB per step) are far larger than the 126 MB L2; no flush needed",
                        "parallelism": f"region shards x{world}, counters all-reduced" if world > 1 else "single GPU", **prep},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_pileup_classify", "kernel_ms": pileup_ms,
+                         "traffic": traffic, "kernel": "k_pileup_classify", "kernel_ms": pileup_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_cell": alg_bytes / cells_expected, "peak_source": peak_src},
             "e2e": {"value": cells_all / (e2e_best * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_best,
