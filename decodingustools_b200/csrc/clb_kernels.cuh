@@ -29,8 +29,8 @@ constexpr int NWARPS = NT / 32;
 #ifndef CLB_MINB
 #define CLB_MINB 4
 #endif
-#ifndef CLB_UNROLL2
-#define CLB_UNROLL2 1
+#ifndef CLB_STAGE
+#define CLB_STAGE 0              // >0: per-thread cp.async staging ring of this many 32-byte slots for the pooled segments
 #endif
 constexpr int PPT = CLB_PPT;          // window entries per thread in the classify phase
 constexpr int WN = NT * PPT;          // entries per window; entry 0 is the halo position (window start - 1)
@@ -40,7 +40,7 @@ constexpr int FAST_OPS = 6;           // CIGAR ops walked lane-serially; longer 
 constexpr int CHUNK_CAP = 352;        // 16-byte quality chunks mapped per warp round
 constexpr int NFIRST = 128;           // low-MAPQ threshold table entries cached in shared memory
 #ifndef CLB_KLQ
-#define CLB_KLQ 6
+#define CLB_KLQ 4
 #endif
 constexpr int KLQ = CLB_KLQ;          // packed-u8 low-BQ arrays per window
 constexpr int BPA = 7;                // 32-read batches per packed array: 7 * 32 = 224 increments max < 256
@@ -235,6 +235,62 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
     }
 }
 
+#if CLB_STAGE > 0
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+    return r;
+}
+
+// Same slot walk as process_slots, but every thread keeps CLB_STAGE slots (32 bytes each) in flight through its own
+// cp.async staging ring in shared memory: the copies need no registers and no barrier (a thread only waits for its own groups).
+template <bool BQ_HI>
+__device__ __forceinline__ void process_slots_staged(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint4 *desc,
+                                                     const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
+                                                     uint32_t &acc_sum, uint32_t &acc_cnt, uint32_t f0, uint32_t stride, uint32_t ring) {
+    const uint32_t total = n_owner * S2;
+    const uint32_t rcp = S2 < (uint32_t)NRCP ? sRcp[S2] : 0xffffffffu / S2 + 1u;
+    const uint8_t *qb = W.qual + W.qbase;
+    auto issue = [&](uint32_t f, uint32_t k) {
+        if (f < total) {
+            const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
+            const uint32_t c = 2u * (f - o * S2);
+            const uint4 d = desc[o];
+            if ((int)((d.x & 15u) + d.z) - (int)(16u * c) > 0) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(qb + (d.x & ~15u)) + c;
+                cp_async16(ring + 32u * k, src); cp_async16(ring + 32u * k + 16u, src + 1);
+            }
+        }
+        cp_async_commit();                                   // always: keeps the group count uniform
+    };
+#pragma unroll
+    for (int k = 0; k < CLB_STAGE; k++) issue(f0 + k * stride, k);
+    uint32_t k = 0;
+    for (uint32_t f = f0; f < total; f += stride) {
+        cp_async_wait<CLB_STAGE - 1>();
+        const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
+        const uint32_t c = 2u * (f - o * S2);
+        const uint4 d = desc[o];
+        const uint32_t head = d.x & 15u;
+        const int rem = (int)(head + d.z) - (int)(16u * c);
+        const uint4 v0 = lds128(ring + 32u * k), v1 = lds128(ring + 32u * k + 16u);
+        issue(f + CLB_STAGE * stride, k);
+        k = k + 1 == CLB_STAGE ? 0 : k + 1;
+        if (rem <= 0) continue;
+        const int e0 = (int)(d.y + 16u * c) - (int)head;
+        const uint32_t lq_arr = sLQ_s + (d.w >> 16) * (uint32_t)(LQ_SLAB * 4);
+        process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
+        process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)max(0, min(rem - 16, 16)), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
+    }
+    cp_async_wait<0>();
+}
+#endif
+
 __device__ __forceinline__ uint32_t seg_chunks(const Seg &s) { return ((s.qrel & 15u) + s.len + 15u) >> 4; }
 
 // Warp-collective: lanes holding a segment (has) publish it compactly into the warp's descriptor area and stream it
@@ -255,12 +311,15 @@ __device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint3
 
 // shared memory: A | B | LQ (KLQ packed-u8 arrays) | masks | first | desc | scan | last | warp stats | next
 constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
-constexpr int DCAP = 1024;            // CTA-wide segment pool (descriptors); a 32-read batch adds at most 64
+#ifndef CLB_DCAP
+#define CLB_DCAP 1024
+#endif
+constexpr int DCAP = CLB_DCAP;        // CTA-wide segment pool (descriptors); a 32-read batch adds at most 64
 constexpr int BPR = DCAP / 64;        // batches per round
 constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 16 + 64 * 4 + NT
-                            + (size_t)NWARPS * N_STATS * 8 + 32;
+                            + (size_t)NWARPS * N_STATS * 8 + 32 + (size_t)CLB_STAGE * 32 * NT;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
-static_assert(SMEM_COUNTER_WORDS % 4 == 0, "counter region is zeroed with 16-byte stores");
+static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region is zeroed with 16-byte stores");
 
 template <bool BQ_HI>
 __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams P) {
@@ -281,6 +340,9 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w = P.win_first + blockIdx.x;
+#if CLB_STAGE > 0
+    const uint32_t sRing = smem_addr(sCtl + 8) + (uint32_t)tid * (32u * CLB_STAGE);     // this thread's staging ring (16-byte aligned)
+#endif
 #define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
     CLB_STAMP(0);
 
@@ -307,8 +369,10 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     }
 
     {
+        // zero the difference arrays and only the low-BQ slabs this window will use
         uint4 *z = reinterpret_cast<uint4 *>(sA);
-        for (int i = tid; i < (int)(SMEM_COUNTER_WORDS / 4); i += NT) z[i] = make_uint4(0, 0, 0, 0);
+        const int nz = (int)((2 * WN + (W.lq_packed ? n_lq : (uint32_t)KLQ) * LQ_SLAB) / 4);
+        for (int i = tid; i < nz; i += NT) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid < 17) {
         uint32_t lo[4], hi[4];
@@ -468,7 +532,11 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     {
         const uint32_t pool_n = ctl[1], pool_s2 = (ctl[2] + 1u) >> 1;
         if (tid < 3) sCtl[3 * ((round + 1) & 1) + tid] = tid == 0 ? rb1 : 0u;     // next round's controls (nobody reads them before the barrier below)
+#if CLB_STAGE > 0
+        process_slots_staged<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT, sRing);
+#else
         process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT);
+#endif
     }
     __syncthreads();                                         // counters final / pool free for the next round
     }
