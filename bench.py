@@ -234,8 +234,17 @@ def main():
 
     keepalive: list = []
     first = e2e_pass()                      # also leaves the contig resident for the HBM-resident leg
+    # size-independent properties of the full-size result (the oracle only sees a bounded sample, below)
     assert first.summed_coverage == cells_expected, (first.summed_coverage, cells_expected)
     assert int(first.state_counts.sum()) == c.length
+    _, chk = ctx.rerun_resident(fetch=True, copy_intervals=True)
+    iv = chk.intervals
+    assert iv["start"][0] == 0 and iv["end"][-1] == c.length and np.array_equal(iv["start"][1:], iv["end"][:-1])
+    assert np.all(iv["state"][1:] != iv["state"][:-1])
+    assert np.array_equal(np.bincount(iv["state"], weights=(iv["end"] - iv["start"]).astype(np.float64), minlength=6).astype(np.int64),
+                          chk.state_counts.astype(np.int64))
+    assert int(chk.bins.sum()) == int(chk.state_counts[0] + chk.state_counts[1] + chk.state_counts[5])
+    n_intervals = int(iv.shape[0]); del iv, chk
 
     def allreduce_counters():
         if world == 1:
@@ -309,7 +318,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u32 integer", "data": "synthetic",
             "config": {"workload": "chr1-size synthetic 30x 2x150bp PE, pileup+classify+BED on one B200 per rank (BASELINE configs[1])",
-                       "contig_bp": c.length, "reads": reads.n, "cells_per_rank": cells_expected, "scale": args.scale,
+                       "contig_bp": c.length, "reads": reads.n, "cells_per_rank": cells_expected, "bed_intervals": n_intervals, "scale": args.scale,
                        "l2_policy": f"inputs ({alg_bytes / 1e9:.2f} GB per step) are far larger than the 126 MB L2; no flush needed",
                        "parallelism": f"region shards x{world}, counters all-reduced" if world > 1 else "single GPU", **prep},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

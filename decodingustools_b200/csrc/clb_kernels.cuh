@@ -21,7 +21,10 @@
 
 namespace clb {
 
-constexpr int NT = 256;               // threads per CTA
+#ifndef CLB_NT
+#define CLB_NT 256
+#endif
+constexpr int NT = CLB_NT;            // threads per CTA
 constexpr int NWARPS = NT / 32;
 #ifndef CLB_PPT
 #define CLB_PPT 8
@@ -317,7 +320,7 @@ constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
 constexpr int DCAP = CLB_DCAP;        // CTA-wide segment pool (descriptors); a 32-read batch adds at most 64
 constexpr int BPR = DCAP / 64;        // batches per round
 constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 16 + 64 * 4 + NT
-                            + (size_t)NWARPS * N_STATS * 8 + 32 + (size_t)CLB_STAGE * 32 * NT;
+                            + (size_t)NWARPS * N_STATS * 8 + 64 + (size_t)CLB_STAGE * 32 * NT;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
 static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region is zeroed with 16-byte stores");
 
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w = P.win_first + blockIdx.x;
 #if CLB_STAGE > 0
-    const uint32_t sRing = smem_addr(sCtl + 8) + (uint32_t)tid * (32u * CLB_STAGE);     // this thread's staging ring (16-byte aligned)
+    const uint32_t sRing = smem_addr(sCtl + 16) + (uint32_t)tid * (32u * CLB_STAGE);     // this thread's staging ring (16-byte aligned)
 #endif
 #define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
     CLB_STAMP(0);
@@ -389,9 +392,16 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         sMaskLo[tid] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         sMaskHi[tid] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
-    if (tid < NFIRST) sFirst[tid] = P.first_tab[tid];
-    if (tid < NRCP) sRcp[tid] = tid > 1 ? 0xffffffffu / (uint32_t)tid + 1u : 0u;
+    for (int i = tid; i < NFIRST; i += NT) sFirst[i] = P.first_tab[i];
+    for (int i = tid; i < NRCP; i += NT) sRcp[i] = i > 1 ? 0xffffffffu / (uint32_t)i + 1u : 0u;
     if (tid < 6) sCtl[tid] = 0;
+    if (tid == 0) {                                          // runtime divisions once per CTA instead of once per thread
+        const uint32_t nr = (n_batches + BPR - 1) / BPR;
+        sCtl[8] = nr; sCtl[9] = nr ? (n_batches + nr - 1) / nr : 0u;
+        const uint32_t first_bin = P.stride ? (uint32_t)(W.wb + 1) / P.stride : 0u;
+        sCtl[10] = first_bin;
+        sCtl[11] = P.stride ? (uint32_t)((long long)(first_bin + 1) * P.stride - W.wb) : 0xffffffffu;   // first entry of the next bin
+    }
     __syncthreads();
 
     CLB_STAMP(1);
@@ -405,8 +415,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     // Rounds of at most BPR batches of 32 reads: (A) walk the CIGARs, update the difference arrays and append the
     // M-segments to the CTA-wide pool; (B) after a barrier ALL warps stream the pooled segments slot by slot,
     // so the quality streaming is balanced across the CTA no matter how the batches fell.
-    const uint32_t n_rounds = (n_batches + BPR - 1) / BPR;
-    const uint32_t bpr = n_rounds ? (n_batches + n_rounds - 1) / n_rounds : 0;
+    const uint32_t n_rounds = sCtl[8], bpr = sCtl[9];
     for (uint32_t round = 0; round < n_rounds; round++) {
     uint32_t *ctl = sCtl + 3 * (round & 1);
     const uint32_t rb1 = min(n_batches, (round + 1) * bpr);
@@ -682,19 +691,19 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         uint32_t inb = nb;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inb, dd); if (lane >= dd) inb += t; }
-        if (lane == 31) sScan[16 + warp] = inb;
+        if (lane == 31) sScan[2 * NWARPS + warp] = inb;
         __syncthreads();
         uint32_t off = inb - nb, total = 0;
 #pragma unroll
-        for (int j = 0; j < NWARPS; j++) { const uint32_t t = sScan[16 + j]; if (j < warp) off += t; total += t; }
+        for (int j = 0; j < NWARPS; j++) { const uint32_t t = sScan[2 * NWARPS + j]; if (j < warp) off += t; total += t; }
         if (tid == 0) {
             const uint32_t base = total ? atomicAdd(P.rec_cursor, total) : 0u;
-            sScan[32] = base;
+            sScan[3 * NWARPS] = base;
             P.win_tab[w] = make_uint2(base, total);
             if (total && (unsigned long long)base + total > P.rec_cap) atomicOr(P.err, ERR_REC_OVERFLOW);
         }
         __syncthreads();
-        uint32_t o = sScan[32] + off;
+        uint32_t o = sScan[3 * NWARPS] + off;
         uint32_t m = bmask;
         while (m) {
             const int k = __ffs(m) - 1; m &= m - 1;
@@ -712,7 +721,12 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         const uint32_t c_call = (cnt_pack >> (5 * ST_CALLABLE)) & 31u, c_poor = (cnt_pack >> (5 * ST_POOR_MAPQ)) & 31u, c_refn = cnt_pack & 31u;
         const uint32_t we0 = max(1u, (uint32_t)(warp * 32 * PPT)), we1 = min(n_ent, (uint32_t)((warp + 1) * 32 * PPT));
         if (we1 > we0) {                                                   // warp-uniform
-            const uint32_t wbin0 = (uint32_t)(W.wb + we0) / P.stride, wbin1 = (uint32_t)(W.wb + we1 - 1) / P.stride;
+            // the window's first bin and the entry where the next bin starts were divided out once by thread 0
+            const uint32_t fb = sCtl[10], nbe = sCtl[11];
+            uint32_t wbin0, wbin1;
+            if (we1 <= nbe) { wbin0 = wbin1 = fb; }
+            else if (we0 >= nbe && we1 - nbe <= P.stride) { wbin0 = wbin1 = fb + 1; }
+            else { wbin0 = (uint32_t)(W.wb + we0) / P.stride; wbin1 = (uint32_t)(W.wb + we1 - 1) / P.stride; }
             if (wbin0 == wbin1) {        // whole warp inside one bin (the common case: stride >> 256)
                 const uint32_t s0 = __reduce_add_sync(FULL, c_call), s1 = __reduce_add_sync(FULL, c_poor), s2 = __reduce_add_sync(FULL, c_refn);
                 if (lane == 0) {

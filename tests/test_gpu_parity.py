@@ -176,3 +176,51 @@ def test_rerun_resident_is_idempotent(ctx_default):
         assert ms > 0
         assert np.array_equal(again.intervals, first.intervals) and np.array_equal(again.state_counts, first.state_counts)
         assert again.summed_baseq == first.summed_baseq and np.array_equal(again.bins, first.bins)
+
+
+def test_whole_genome_layout_tiny_scale(ctx_default):
+    """BASELINE config 3 shape: 24 contigs + chrM in tid order, quirks Q1/Q2 across every contig boundary."""
+    contigs = synth.config(2, scale=0.0015)
+    assert len(contigs) == 25 and contigs[-1].name == "chrM"
+    assert_parity([(c.name, tid, c.length, c.ref, c.reads) for tid, c in enumerate(contigs)], CallableOptions(), ctx_default)
+
+
+def test_device_computed_span_and_nmask_reference(ctx_default):
+    """max_ref_span = 0 lets the library compute the look-back on the device; the reference may come as a bit-packed N mask."""
+    from decodingustools_b200.callable_loci import compact_reads
+    from decodingustools_b200.soa import n_mask_from_ascii
+    c = synth.synth_short("chr22", 300_000, seed=31)
+    reads = compact_reads(c.reads, admit_reads(c.reads, 500, 0))
+    ctx_default.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
+    ctx_default.push_reads(reads)
+    want = ctx_default.finish_contig()
+    ctx_default.begin_contig(0, c.name, c.length, n_mask_from_ascii(c.ref), c.length, max_ref_span=0, ref_is_nmask=True)
+    for lo in range(0, reads.n, 20_000):
+        ctx_default.push_reads(reads.slice(lo, lo + 20_000))
+    got = ctx_default.finish_contig()
+    assert np.array_equal(got.intervals, want.intervals) and np.array_equal(got.state_counts, want.state_counts)
+    assert np.array_equal(got.bins, want.bins) and got.summed_baseq == want.summed_baseq and got.summed_mapq == want.summed_mapq
+
+
+def test_reference_shorter_than_contig_reads_as_n(ctx_default):
+    """fetch_seq past the FASTA end yields nothing -> 'N' (mod.rs:79-80)."""
+    reads = ReadColumns.from_records([(p, 0, 60, "50M", 30, f"r{p}_{k}") for p in range(0, 150, 10) for k in range(5)])
+    assert_parity([("c", 0, 300, b"ACGT" * 30, reads)], CallableOptions(), ctx_default)
+
+
+def test_intervals_tile_the_contig_and_alternate(ctx_default):
+    """Size-independent properties used at full size by bench.py."""
+    c = synth.synth_short("chr22", 2_000_000, seed=33)
+    from decodingustools_b200.callable_loci import compact_reads
+    reads = compact_reads(c.reads, admit_reads(c.reads, 500, 0))
+    ctx_default.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
+    ctx_default.push_reads(reads)
+    r = ctx_default.finish_contig()
+    iv = r.intervals
+    assert iv["start"][0] == 0 and iv["end"][-1] == c.length
+    assert np.array_equal(iv["start"][1:], iv["end"][:-1]) and np.all(iv["state"][1:] != iv["state"][:-1])
+    assert int(r.state_counts.sum()) == c.length
+    lens = (iv["end"] - iv["start"]).astype(np.int64)
+    assert np.array_equal(np.bincount(iv["state"], weights=lens, minlength=6).astype(np.int64), r.state_counts.astype(np.int64))
+    assert r.summed_coverage == int(reads.ref_len().sum())
+    assert r.n_covered_bases >= int(r.state_counts[1] + r.state_counts[3] + r.state_counts[4] + r.state_counts[5])
