@@ -182,19 +182,18 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
     const uint32_t ONES = 0x01010101u;
     // dot products against the 0x80 flags give 128 x (count, sum) of the failing bytes
     const uint32_t tot = __dp4a(v.x, ONES, __dp4a(v.y, ONES, __dp4a(v.z, ONES, __dp4a(v.w, ONES, 0u))));
-    const uint32_t nf128 = __dp4a(l0, ONES, __dp4a(l1, ONES, __dp4a(l2, ONES, __dp4a(l3, ONES, 0u))));
     const uint32_t sf128 = __dp4a(v.x, l0, __dp4a(v.y, l1, __dp4a(v.z, l2, __dp4a(v.w, l3, 0u))));
     const uint32_t ninv = lo + (16u - hi);
     acc_sum += tot - 255u * ninv - (sf128 >> 7);
-    acc_cnt += 16u - ninv - (nf128 >> 7);
+#ifdef CLB_COUNT_CHECK
+    acc_cnt += 16u - ninv - (__dp4a(l0, ONES, __dp4a(l1, ONES, __dp4a(l2, ONES, __dp4a(l3, ONES, 0u)))) >> 7);
+#endif
     const uint32_t f0 = l0 >> 7, f1 = l1 >> 7, f2 = l2 >> 7, f3 = l3 >> 7;                    // 1 in every failing byte
     if (W.lq_packed) {
         // four positions per 32-bit word, one byte each: shift the 16 fail flags to the entry alignment and add them
-        // with five unconditional atomics (a byte takes <= 224 increments, see BPA).  Out-of-window chunks carry no
-        // flags; their address is clamped into the array.
-        const int ec = max(-16, min(e0, WN));
-        const uint32_t sh = ((uint32_t)ec & 3u) << 3;
-        const uint32_t base = lq_arr + 64u + (uint32_t)((ec >> 2) * 4);      // arrays start 16 words into their slab
+        // with five unconditional atomics (a byte takes <= 224 increments, see BPA).
+        const uint32_t sh = ((uint32_t)e0 & 3u) << 3;
+        const uint32_t base = lq_arr + 64u + (uint32_t)((e0 >> 2) * 4);      // arrays start 16 words into their slab (e0 >= -15)
         red_shared(base + 0, f0 << sh);
         red_shared(base + 4, __funnelshift_l(f0, f1, sh));
         red_shared(base + 8, __funnelshift_l(f1, f2, sh));
@@ -229,12 +228,16 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
         const int rem = (int)(head + d.z) - (int)(16u * c);            // bytes from chunk c's start to the segment end
         if (rem <= 0) continue;
         const uint4 *src = reinterpret_cast<const uint4 *>(qb + (d.x & ~15u)) + c;
+#ifdef CLB_EXPERIMENT_NOLOAD
+        const uint4 v0 = make_uint4(0x25252525u + (uint32_t)(size_t)src, 0x25250225u, 0x25252525u, 0x25252525u), v1 = v0;   // timing experiment only
+#else
         const uint4 v0 = ldg_stream(src);
         const uint4 v1 = ldg_stream(src + 1);                             // may lie past the segment (buffers are padded): masked below
+#endif
         const int e0 = (int)(d.y + 16u * c) - (int)head;
         const uint32_t lq_arr = sLQ_s + (d.w >> 16) * (uint32_t)(LQ_SLAB * 4);
         process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
-        process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)max(0, min(rem - 16, 16)), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
+        if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
     }
 }
 
@@ -288,7 +291,7 @@ __device__ __forceinline__ void process_slots_staged(const Win &W, uint32_t sLQ_
         const int e0 = (int)(d.y + 16u * c) - (int)head;
         const uint32_t lq_arr = sLQ_s + (d.w >> 16) * (uint32_t)(LQ_SLAB * 4);
         process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
-        process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)max(0, min(rem - 16, 16)), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
+        if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
     }
     cp_async_wait<0>();
 }
