@@ -1,0 +1,443 @@
+// coverage_cli.cpp -- `decodingus-tools-b200 coverage`: the reference's `coverage` command on the B200 path.
+//
+// Host side of the drop-in, written in C++ because this image has no
+// Rust toolchain; it only talks to the device through the C ABI of include/callable_loci_b200.h, exactly as a Rust
+// host would.  Mirrors, with citations into /root/reference:
+//   flags and defaults                     src/cli.rs:14-61
+//   run_analysis / contig selection        src/api/coverage.rs:53-115,149-236 (ascending tid, largest non-chrM length)
+//   process_single_contig                  src/callable_loci/mod.rs:44-147 (per-base loop replaced by the device)
+//   build_coverage_export / natural order  src/callable_loci/report.rs:15-134,337-393
+//   get_quality_stats                      src/callable_loci/profilers/contig_profiler.rs:123-158
+//   summary.json (written in the CWD)      src/main.rs:67-69, src/export/formats/coverage.rs (field order)
+//   detect_aligner / reference build       src/callable_loci/mod.rs:149-177, src/types.rs:100-147
+//   BamStats read length (first 10 000)    src/callable_loci/profilers/bam_stats.rs:60-76,187-193
+// What rust-htslib did (BGZF inflate, BAM record decode, faidx) is done here: multi-threaded zlib inflate of BGZF blocks,
+// a sequential record scan (the file is coordinate sorted, so no .bai is needed) and an in-memory FASTA contig load.
+// Not produced: the HTML report and the SVG plots (rows N2-HTML/N3), sequencing-platform inference (N4) -> "Unknown".
+#include "../../../include/callable_loci_b200.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void die(const std::string &m) { fprintf(stderr, "Error: %s\n", m.c_str()); exit(1); }
+
+// ------------------------------------------------------------------------------------------------ BGZF / BAM
+struct BamHeader { std::string text; std::vector<std::string> names; std::vector<uint32_t> lens; };
+
+struct BamRecordView {
+    int32_t tid, pos; uint8_t mapq; uint16_t flag; uint16_t n_cigar; int32_t l_seq;
+    const char *qname; uint32_t l_qname; const uint32_t *cigar; const uint8_t *qual;
+};
+
+class BgzfStream {
+  public:
+    BgzfStream(const std::string &path, unsigned threads) : threads_(std::max(1u, threads)) {
+        fp_ = fopen(path.c_str(), "rb");
+        if (!fp_) die("Failed to open BAM file: " + path);
+        cbuf_.reserve(kChunk + (1 << 17));
+    }
+    ~BgzfStream() { if (fp_) fclose(fp_); }
+    // Appends the next batch of inflated bytes to out; returns false at EOF.
+    bool next(std::vector<uint8_t> &out) {
+        if (eof_ && cbuf_.empty()) return false;
+        const size_t have = cbuf_.size();
+        cbuf_.resize(have + kChunk);
+        const size_t got = eof_ ? 0 : fread(cbuf_.data() + have, 1, kChunk, fp_);
+        cbuf_.resize(have + got);
+        if (got < kChunk) eof_ = true;
+        struct Blk { size_t off, clen, ulen, uoff; };
+        std::vector<Blk> blks; size_t o = 0, utotal = 0;
+        while (o + 18 <= cbuf_.size()) {
+            const uint8_t *p = cbuf_.data() + o;
+            if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) die("not a BGZF file (bad block header)");
+            const uint32_t xlen = p[10] | (p[11] << 8);
+            if (o + 12 + xlen > cbuf_.size()) break;
+            uint32_t bsize = 0; bool found = false;
+            for (uint32_t x = 0; x + 4 <= xlen;) {
+                const uint8_t *s = p + 12 + x; const uint32_t sl = s[2] | (s[3] << 8);
+                if (s[0] == 'B' && s[1] == 'C' && sl == 2) { bsize = (s[4] | (s[5] << 8)) + 1u; found = true; }
+                x += 4 + sl;
+            }
+            if (!found) die("BGZF block without BC field");
+            if (o + bsize > cbuf_.size()) break;
+            const uint8_t *tail = p + bsize - 4;
+            const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+            blks.push_back({o + 12 + xlen, bsize - 12 - xlen - 8, isize, utotal});
+            utotal += isize; o += bsize;
+        }
+        if (blks.empty() && !cbuf_.empty() && eof_) die("truncated BGZF file");
+        const size_t base = out.size();
+        out.resize(base + utotal);
+        std::vector<std::thread> pool; std::vector<int> err(threads_, 0);
+        for (unsigned t = 0; t < threads_; t++)
+            pool.emplace_back([&, t] {
+                for (size_t i = t; i < blks.size(); i += threads_) {
+                    if (!blks[i].ulen) continue;
+                    z_stream zs; memset(&zs, 0, sizeof zs);
+                    if (inflateInit2(&zs, -15) != Z_OK) { err[t] = 1; return; }
+                    zs.next_in = cbuf_.data() + blks[i].off; zs.avail_in = (uInt)blks[i].clen;
+                    zs.next_out = out.data() + base + blks[i].uoff; zs.avail_out = (uInt)blks[i].ulen;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    inflateEnd(&zs);
+                    if (rc != Z_STREAM_END || zs.avail_out != 0) { err[t] = 1; return; }
+                }
+            });
+        for (auto &th : pool) th.join();
+        for (int e : err) if (e) die("BGZF inflate failed");
+        cbuf_.erase(cbuf_.begin(), cbuf_.begin() + (long)o);
+        return true;
+    }
+
+  private:
+    static constexpr size_t kChunk = 64u << 20;
+    FILE *fp_ = nullptr; unsigned threads_; bool eof_ = false;
+    std::vector<uint8_t> cbuf_;
+};
+
+class BamReader {
+  public:
+    BamReader(const std::string &path, unsigned threads) : bz_(path, threads) {
+        need(12);
+        if (memcmp(cur(), "BAM\1", 4) != 0) die("Failed to open BAM file: not a BAM (CRAM is not supported by this host)");
+        const int32_t l_text = rd32(4); need(12 + (size_t)l_text);
+        hdr_.text.assign((const char *)cur() + 8, (size_t)l_text);
+        const int32_t n_ref = rd32(8 + l_text); off_ += 12 + (size_t)l_text;
+        for (int32_t i = 0; i < n_ref; i++) {
+            need(4); const int32_t l_name = rd32(0); need(8 + (size_t)l_name);
+            hdr_.names.emplace_back((const char *)cur() + 4, (size_t)std::max(0, l_name - 1));
+            hdr_.lens.push_back((uint32_t)rd32(4 + l_name));
+            off_ += 8 + (size_t)l_name;
+        }
+    }
+    const BamHeader &header() const { return hdr_; }
+    bool next(BamRecordView &r) {
+        if (!need(4)) return false;
+        const int32_t bs = rd32(0);
+        if (bs < 32 || !need(4 + (size_t)bs)) die("truncated BAM record");
+        const uint8_t *p = cur() + 4;
+        auto i32 = [&](int o) { int32_t v; memcpy(&v, p + o, 4); return v; };
+        auto u16 = [&](int o) { uint16_t v; memcpy(&v, p + o, 2); return v; };
+        r.tid = i32(0); r.pos = i32(4); r.l_qname = p[8]; r.mapq = p[9]; r.n_cigar = u16(12); r.flag = u16(14); r.l_seq = i32(16);
+        r.qname = (const char *)p + 32;
+        r.cigar = (const uint32_t *)(p + 32 + r.l_qname);
+        r.qual = p + 32 + r.l_qname + 4 * (size_t)r.n_cigar + ((size_t)r.l_seq + 1) / 2;
+        off_ += 4 + (size_t)bs;
+        return true;
+    }
+
+  private:
+    const uint8_t *cur() const { return buf_.data() + off_; }
+    int32_t rd32(size_t o) const { int32_t v; memcpy(&v, cur() + o, 4); return v; }
+    bool need(size_t n) {
+        while (buf_.size() - off_ < n) {
+            if (off_ > (32u << 20)) { buf_.erase(buf_.begin(), buf_.begin() + (long)off_); off_ = 0; }
+            if (!bz_.next(buf_)) return false;
+        }
+        return true;
+    }
+    BgzfStream bz_; std::vector<uint8_t> buf_; size_t off_ = 0; BamHeader hdr_;
+};
+
+// ------------------------------------------------------------------------------------------------ FASTA
+struct FaiEntry { uint64_t len, offset; uint32_t linebases, linewidth; };
+std::map<std::string, FaiEntry> load_fai(const std::string &fasta) {
+    std::map<std::string, FaiEntry> m;
+    std::ifstream in(fasta + ".fai");
+    if (!in) die("Failed to open reference: " + fasta + ".fai is missing (the reference also requires it, api/coverage.rs:73)");
+    std::string name; FaiEntry e;
+    while (in >> name >> e.len >> e.offset >> e.linebases >> e.linewidth) { m[name] = e; in.ignore(1 << 20, '\n'); }
+    return m;
+}
+std::vector<uint8_t> load_contig(const std::string &fasta, const FaiEntry &e) {
+    std::vector<uint8_t> seq; seq.reserve(e.len);
+    FILE *fp = fopen(fasta.c_str(), "rb");
+    if (!fp) die("Failed to open reference: " + fasta);
+    const uint64_t lines = e.linebases ? (e.len + e.linebases - 1) / e.linebases : 0;
+    std::vector<uint8_t> raw((size_t)(lines * e.linewidth + 16));
+    fseeko(fp, (off_t)e.offset, SEEK_SET);
+    const size_t got = fread(raw.data(), 1, raw.size(), fp);
+    fclose(fp);
+    for (size_t i = 0; i < got && seq.size() < e.len; i++) if (raw[i] != '\n' && raw[i] != '\r') seq.push_back(raw[i]);
+    return seq;
+}
+
+// ------------------------------------------------------------------------------------------------ report
+struct ContigStats {            // ContigProfiler + CallableProfiler::contig_counts
+    std::string name; uint64_t length = 0;
+    uint64_t counts[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t n_covered = 0, sum_cov = 0, sum_bq = 0, sum_mapq = 0, qbases = 0, n_reads = 0;
+};
+
+size_t split_pos(const std::string &s) {
+    for (size_t i = 0; i < s.size(); i++) if (isdigit((unsigned char)s[i]) || s[i] == 'X' || s[i] == 'Y' || s[i] == 'M') return i;
+    return s.size();
+}
+void order_key(const std::string &suf, unsigned &cat, uint32_t &num) {
+    const char *p = suf.c_str(); if (*p == '+') p++;
+    bool ok = *p != 0; uint64_t v = 0;
+    for (const char *q = p; *q; q++) { if (*q < '0' || *q > '9') { ok = false; break; } v = v * 10 + (uint64_t)(*q - '0'); if (v > 0xffffffffull) { ok = false; break; } }
+    num = 0;
+    if (ok) { cat = 0; num = (uint32_t)v; return; }
+    cat = suf == "X" ? 1 : suf == "Y" ? 2 : (suf == "M" || suf == "MT") ? 3 : 4;
+}
+bool contig_less(const std::string &a, const std::string &b) {     // report.rs:339-383
+    const size_t sa = split_pos(a), sb = split_pos(b);
+    const std::string pa = a.substr(0, sa), pb = b.substr(0, sb);
+    if (pa != pb) return pa < pb;
+    unsigned ca, cb; uint32_t na, nb;
+    order_key(a.substr(sa), ca, na); order_key(b.substr(sb), cb, nb);
+    if (ca != cb) return ca < cb;
+    if (ca == 0) return na < nb;
+    return a.substr(sa) < b.substr(sb);
+}
+
+// serde_json / ryu formatting of an f64: shortest round-trip digits, ".0" for integers, exponent outside 1e-5..1e16
+std::string fmt_f64(double v) {
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    std::string s(buf, res.ptr);                           // d[.ddd]e[+-]xx
+    const size_t epos = s.find('e');
+    std::string mant = s.substr(0, epos); const int exp10 = atoi(s.c_str() + epos + 1);
+    const bool neg = mant[0] == '-'; if (neg) mant.erase(0, 1);
+    std::string digits; for (char ch : mant) if (ch != '.') digits.push_back(ch);
+    const int nd = (int)digits.size(), kk = exp10 + 1;     // decimal point position relative to digits
+    std::string out;
+    if (v == 0) out = "0.0";
+    else if (nd <= kk && kk <= 16) { out = digits + std::string((size_t)(kk - nd), '0') + ".0"; }
+    else if (0 < kk && kk <= 16) { out = digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk); }
+    else if (-5 < kk && kk <= 0) { out = "0." + std::string((size_t)(-kk), '0') + digits; }
+    else { out = digits.substr(0, 1) + (nd > 1 ? "." + digits.substr(1) : "") + "e" + std::to_string(exp10); }
+    return (neg ? "-" : "") + out;
+}
+std::string jstr(const std::string &s) {
+    std::string o = "\"";
+    for (char ch : s) { if (ch == '"' || ch == '\\') { o += '\\'; o += ch; } else if (ch == '\n') o += "\\n"; else if (ch == '\t') o += "\\t"; else o += ch; }
+    return o + "\"";
+}
+
+std::string detect_aligner(const std::string &header_text) {       // callable_loci/mod.rs:149-177
+    std::string h = header_text; for (auto &c : h) c = (char)tolower((unsigned char)c);
+    auto has = [&](const char *s) { return h.find(s) != std::string::npos; };
+    if (has("@pg\tid:bwa-mem2")) return "BWA-MEM2";
+    if (has("@pg\tid:bwa")) return "BWA";
+    if (has("@pg\tid:minimap2")) return "minimap2";
+    if (has("@pg\tid:pbmm2")) return "pbmm2";
+    if (has("@pg\tid:bowtie2")) return "Bowtie2";
+    if (has("@pg\tid:star")) return "STAR";
+    if (has("bwa")) return "BWA";
+    if (has("minimap2")) return "minimap2";
+    if (has("bowtie2")) return "Bowtie2";
+    if (has("star")) return "STAR";
+    return "Unknown";
+}
+std::string reference_build(const std::string &t) {                // types.rs:100-147
+    auto has = [&](const char *s) { return t.find(s) != std::string::npos; };
+    if (has("AS:GRCh38") || has("GCA_000001405.15")) return "GRCh38";
+    if (has("AS:GRCh37") || has("GCA_000001405.1")) return "GRCh37";
+    if (has("AS:CHM13") || has("GCA_009914755.4") || has("chm13") || has("CHM13") || has("t2t") || has("T2T")) return "T2T-CHM13v2.0";
+    if (has("SN:chr1") && has("LN:248387328") && has("M5:e469247288ceb332aee524caec92bb22")) return "T2T-CHM13v2.0";
+    if (has("SN:chr1") && has("LN:248956422")) return "GRCh38";
+    if (has("SN:1") && has("LN:249250621")) return "GRCh37";
+    return "Unknown";
+}
+
+struct Columns {
+    std::vector<int32_t> pos; std::vector<uint16_t> flag; std::vector<uint8_t> mapq;
+    std::vector<uint32_t> cigar_off{0}, cigar; std::vector<uint64_t> qual_off{0}; std::vector<uint8_t> qual;
+    std::vector<uint32_t> name_off{0}; std::vector<char> names;
+    void clear() { pos.clear(); flag.clear(); mapq.clear(); cigar_off.assign(1, 0); cigar.clear(); qual_off.assign(1, 0); qual.clear(); name_off.assign(1, 0); names.clear(); }
+    void push(const BamRecordView &r) {
+        pos.push_back(r.pos); flag.push_back(r.flag); mapq.push_back(r.mapq);
+        cigar.insert(cigar.end(), r.cigar, r.cigar + r.n_cigar); cigar_off.push_back((uint32_t)cigar.size());
+        qual.insert(qual.end(), r.qual, r.qual + std::max(0, r.l_seq)); qual_off.push_back(qual.size());
+        const uint32_t ln = r.l_qname ? r.l_qname - 1 : 0;
+        names.insert(names.end(), r.qname, r.qname + ln); name_off.push_back((uint32_t)names.size());
+    }
+};
+
+uint64_t count_unique_names(const Columns &c, const std::vector<uint8_t> &keep, uint32_t contig_len) {
+    // exact distinct QNAME count among admitted records that reach >= 1 column (contig_profiler.rs:59-62)
+    std::vector<uint32_t> idx;
+    for (size_t i = 0; i < c.pos.size(); i++) {
+        if (!keep[i] || (uint32_t)c.pos[i] >= contig_len) continue;
+        uint64_t span = 0;
+        for (uint32_t k = c.cigar_off[i]; k < c.cigar_off[i + 1]; k++) { const uint32_t op = c.cigar[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c.cigar[k] >> 4; }
+        if (span) idx.push_back((uint32_t)i);
+    }
+    auto view = [&](uint32_t i) { return std::string_view(c.names.data() + c.name_off[i], c.name_off[i + 1] - c.name_off[i]); };
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return view(a) < view(b); });
+    uint64_t n = 0;
+    for (size_t i = 0; i < idx.size(); i++) if (i == 0 || view(idx[i]) != view(idx[i - 1])) n++;
+    return n;
+}
+
+struct Options {
+    std::string bam, reference, out_bed = "callable_regions.bed", summary = "summary.html";
+    std::vector<std::string> contigs; bool have_contigs = false;
+    clb_options o{4, 500, 10, 10, 20, 1, 0, 0.1};
+    unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    int device = 0;
+};
+
+void usage() {
+    fprintf(stderr, "Usage: decodingus-tools-b200 coverage <BAM_FILE> -r <REFERENCE> [-o callable_regions.bed] [-s summary.html] [-L contig]...\n"
+                    "       [--min-depth 4] [--max-depth 500] [--min-mapping-quality 10] [--min-base-quality 20]\n"
+                    "       [--min-depth-for-low-mapq 10] [--max-low-mapq 1] [--max-low-mapq-fraction 0.1] [--threads N] [--device D]\n");
+    exit(2);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 3 || strcmp(argv[1], "coverage") != 0) usage();
+    Options opt;
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) usage(); return argv[++i]; };
+        if (a == "-r" || a == "--reference") opt.reference = val();
+        else if (a == "-o" || a == "--output") opt.out_bed = val();
+        else if (a == "-s" || a == "--summary") opt.summary = val();
+        else if (a == "-L" || a == "--contig") { opt.contigs.push_back(val()); opt.have_contigs = true; }
+        else if (a == "--min-depth") opt.o.min_depth = (uint32_t)std::stoul(val());
+        else if (a == "--max-depth") opt.o.max_depth = (uint32_t)std::stoul(val());
+        else if (a == "--min-mapping-quality") opt.o.min_mapping_quality = (uint8_t)std::stoul(val());
+        else if (a == "--min-base-quality") opt.o.min_base_quality = (uint8_t)std::stoul(val());
+        else if (a == "--min-depth-for-low-mapq") opt.o.min_depth_for_low_mapq = (uint32_t)std::stoul(val());
+        else if (a == "--max-low-mapq") opt.o.max_low_mapq = (uint8_t)std::stoul(val());
+        else if (a == "--max-low-mapq-fraction") opt.o.max_low_mapq_fraction = std::stod(val());
+        else if (a == "--threads") opt.threads = (unsigned)std::stoul(val());
+        else if (a == "--device") opt.device = std::stoi(val());
+        else if (!a.empty() && a[0] != '-' && opt.bam.empty()) opt.bam = a;
+        else usage();
+    }
+    if (opt.bam.empty() || opt.reference.empty()) usage();
+
+    BamReader bam(opt.bam, opt.threads);
+    const BamHeader &H = bam.header();
+    const auto fai = load_fai(opt.reference);
+
+    // initialize_contig_stats + validate_contig_selection (api/coverage.rs:149-204)
+    std::set<std::string> selected(opt.contigs.begin(), opt.contigs.end());
+    std::map<int32_t, ContigStats> stats;
+    for (size_t tid = 0; tid < H.names.size(); tid++) {
+        if (opt.have_contigs && !selected.count(H.names[tid])) continue;
+        ContigStats s; s.name = H.names[tid]; s.length = H.lens[tid];
+        stats[(int32_t)tid] = s;
+    }
+    if (opt.have_contigs && stats.empty()) {
+        std::string l; for (size_t i = 0; i < opt.contigs.size(); i++) l += (i ? ", " : "") + opt.contigs[i];
+        die("None of the specified contigs (" + l + ") were found in the BAM file");
+    }
+    uint32_t largest = 0;                                               // initialize_counter (api/coverage.rs:206-219)
+    for (auto &kv : stats) if (kv.second.name != "chrM") largest = std::max<uint32_t>(largest, (uint32_t)kv.second.length);
+
+    char err[512];
+    clb_ctx *ctx = clb_create(opt.device, &opt.o, err, sizeof err);
+    if (!ctx) die(std::string("GPU context: ") + err);
+    clb_bed_writer *bed = clb_bed_writer_open(opt.out_bed.c_str(), largest);
+    if (!bed) die("Failed to create CallableProfiler: cannot create " + opt.out_bed);
+    auto check = [&](int rc, const char *what) { if (rc != 0) die(std::string("Error processing contig: ") + what + ": " + clb_last_error(ctx)); };
+
+    // BamStats: first 10 000 records, primary alignments only (bam_stats.rs:60-76)
+    uint64_t bs_seen = 0, bs_reads = 0, bs_len = 0;
+
+    Columns cols; BamRecordView rec; bool have = bam.next(rec);
+    const uint32_t maxcnt = opt.o.max_depth > 0 ? opt.o.max_depth : 500;
+    for (auto &kv : stats) {                                           // ascending tid (api/coverage.rs:229-235)
+        const int32_t tid = kv.first; ContigStats &st = kv.second;
+        cols.clear();
+        while (have && (rec.tid < tid && rec.tid >= 0)) {               // records of contigs that were not selected
+            if (bs_seen++ < 10000 && !(rec.flag & 0x900)) { bs_reads++; bs_len += (uint64_t)std::max(0, rec.l_seq); }
+            have = bam.next(rec);
+        }
+        while (have && rec.tid == tid) {
+            if (bs_seen++ < 10000 && !(rec.flag & 0x900)) { bs_reads++; bs_len += (uint64_t)std::max(0, rec.l_seq); }
+            cols.push(rec);
+            have = bam.next(rec);
+        }
+        const uint32_t clen = (uint32_t)st.length;
+        std::vector<uint8_t> ref;
+        auto fe = fai.find(st.name);
+        if (fe != fai.end()) ref = load_contig(opt.reference, fe->second);   // missing contig / short sequence reads as 'N'
+        const size_t n = cols.pos.size();
+        std::vector<uint8_t> keep(n ? n : 1, 0);
+        if (clb_admit_reads(tid, maxcnt, n, cols.pos.data(), cols.flag.data(), cols.cigar_off.data(), cols.cigar.data(), keep.data()) != 0)
+            die("Error processing contig: records are not coordinate sorted");
+        st.n_reads = count_unique_names(cols, keep, clen);
+        clb_read_batch in{n, cols.cigar.size(), cols.qual.size(), cols.pos.data(), cols.flag.data(), cols.mapq.data(),
+                          cols.cigar_off.data(), cols.cigar.data(), cols.qual_off.data(), cols.qual.data()};
+        std::vector<int32_t> p2(n ? n : 1); std::vector<uint16_t> f2(n ? n : 1); std::vector<uint8_t> m2(n ? n : 1), q2(cols.qual.size() + 1);
+        std::vector<uint32_t> co2(n + 1), c2(cols.cigar.size() + 1); std::vector<uint64_t> qo2(n + 1);
+        clb_read_batch adm{};
+        check(clb_compact_reads(&in, keep.data(), p2.data(), f2.data(), m2.data(), co2.data(), c2.data(), qo2.data(), q2.data(), &adm), "compact");
+        check(clb_begin_contig(ctx, tid, st.name.c_str(), clen, ref.data(), ref.size(), 0, largest, 0, clen, 0), "begin");
+        if (adm.n_reads) check(clb_push_reads(ctx, &adm), "push");
+        clb_contig_result res{};
+        check(clb_finish_contig(ctx, &res), "finish");
+        for (int s = 0; s < 6; s++) st.counts[s] = res.state_counts[s];
+        st.n_covered = res.n_covered_bases; st.sum_cov = res.summed_coverage; st.sum_bq = res.summed_baseq;
+        st.sum_mapq = res.summed_mapq; st.qbases = res.quality_bases;
+        std::vector<uint32_t> bins(res.bins, res.bins + 3 * (size_t)res.n_bins);
+        if (clb_bed_writer_add_contig(bed, st.name.c_str(), clen, res.intervals, res.n_intervals, bins.data(), res.n_bins, res.stride, nullptr) != 0)
+            die("Error processing contig: interval list does not tile the contig");
+        fprintf(stderr, "%s: %llu admitted reads, %llu cells, %.2f ms on device\n", st.name.c_str(), (unsigned long long)adm.n_reads,
+                (unsigned long long)res.summed_coverage, res.kernel_ms);
+    }
+    while (have && bs_seen < 10000) { if (!(rec.flag & 0x900)) { bs_reads++; bs_len += (uint64_t)std::max(0, rec.l_seq); } bs_seen++; have = bam.next(rec); }
+    if (clb_bed_writer_close(bed) != 0) die("failed to write " + opt.out_bed);
+    clb_destroy(ctx);
+
+    // build_coverage_export (report.rs:15-134)
+    std::vector<const ContigStats *> order;
+    for (auto &kv : stats) order.push_back(&kv.second);
+    std::stable_sort(order.begin(), order.end(), [](const ContigStats *a, const ContigStats *b) { return contig_less(a->name, b->name); });
+    uint64_t total_bases = 0, callable = 0, q30_bases = 0, total_qpos = 0, total_unique = 0;
+    double total_depth = 0, total_mapq = 0, total_baseq = 0;
+    std::string cj;
+    for (size_t i = 0; i < order.size(); i++) {
+        const ContigStats &s = *order[i];
+        const double amq = s.qbases ? (double)s.sum_mapq / (double)s.qbases : 0.0, abq = s.qbases ? (double)s.sum_bq / (double)s.qbases : 0.0;
+        const double q30 = s.qbases ? (abq >= 30.0 ? 100.0 : abq < 20.0 ? 0.0 : ((abq - 20.0) / 10.0) * 100.0) : 0.0;
+        const double covp = s.length ? ((double)s.n_covered / (double)s.length) * 100.0 : 0.0;
+        const double adep = s.n_covered ? (double)s.sum_cov / (double)s.n_covered : 0.0;
+        total_bases += s.length; callable += s.counts[CLB_CALLABLE];
+        total_depth += adep * (double)s.length; total_mapq += amq * (double)s.length; total_baseq += abq * (double)s.length;
+        q30_bases += (uint64_t)(q30 / 100.0 * (double)s.length); total_qpos += s.length; total_unique += (uint32_t)s.n_reads;
+        cj += std::string(i ? ",\n" : "") + "      {\n        \"name\": " + jstr(s.name) + ",\n        \"length\": " + std::to_string(s.length) +
+              ",\n        \"unique_reads\": " + std::to_string(s.n_reads) + ",\n        \"coverage_percent\": " + fmt_f64(covp) +
+              ",\n        \"average_depth\": " + fmt_f64(adep) + ",\n        \"covered_bases\": " + std::to_string(s.n_covered) +
+              ",\n        \"total_bases\": " + std::to_string(s.length) + ",\n        \"quality_stats\": {\n          \"average_mapq\": " + fmt_f64(amq) +
+              ",\n          \"average_baseq\": " + fmt_f64(abq) + ",\n          \"q30_percentage\": " + fmt_f64(q30) +
+              "\n        },\n        \"state_distribution\": {\n          \"ref_n\": " + std::to_string(s.counts[0]) + ",\n          \"callable\": " +
+              std::to_string(s.counts[1]) + ",\n          \"no_coverage\": " + std::to_string(s.counts[2]) + ",\n          \"low_coverage\": " +
+              std::to_string(s.counts[3]) + ",\n          \"excessive_coverage\": " + std::to_string(s.counts[4]) +
+              ",\n          \"poor_mapping_quality\": " + std::to_string(s.counts[5]) + "\n        }\n      }";
+    }
+    const double avg_depth = total_bases ? total_depth / (double)total_bases : 0.0;
+    const double call_pct = total_bases ? ((double)callable / (double)total_bases) * 100.0 : 0.0;
+    std::string js = "{\n  \"export\": {\n    \"summary\": {\n      \"aligner\": " + jstr(detect_aligner(H.text)) + ",\n      \"reference_build\": " +
+        jstr(reference_build(H.text)) + ",\n      \"sequencing_platform\": \"Unknown\",\n      \"read_length\": " + std::to_string(bs_reads ? bs_len / bs_reads : 0) +
+        ",\n      \"total_bases\": " + std::to_string(total_bases) + ",\n      \"callable_bases\": " + std::to_string(callable) +
+        ",\n      \"callable_percentage\": " + fmt_f64(call_pct) + ",\n      \"average_depth\": " + fmt_f64(avg_depth) + ",\n      \"contigs_analyzed\": " +
+        std::to_string(stats.size()) + "\n    },\n    \"contigs\": [" + (order.empty() ? "" : "\n" + cj + "\n    ") + "],\n    \"quality_metrics\": {\n      \"average_mapq\": " +
+        fmt_f64(total_qpos ? total_mapq / (double)total_qpos : 0.0) + ",\n      \"average_baseq\": " + fmt_f64(total_qpos ? total_baseq / (double)total_qpos : 0.0) +
+        ",\n      \"q30_percentage\": " + fmt_f64(total_qpos ? ((double)q30_bases / (double)total_qpos) * 100.0 : 0.0) + "\n    },\n    \"total_unique_reads\": " +
+        std::to_string(total_unique) + "\n  },\n  \"files\": {\n    \"bed_file\": " + jstr(opt.out_bed) + ",\n    \"summary_html\": " + jstr(opt.summary) +
+        ",\n    \"coverage_plots\": []\n  }\n}";
+    FILE *fj = fopen("summary.json", "wb");                                  // main.rs:68: always in the CWD
+    if (!fj) die("cannot create summary.json");
+    fwrite(js.data(), 1, js.size(), fj); fclose(fj);
+    return 0;
+}
