@@ -118,7 +118,7 @@ class ClockSampler:
 def make_workload(scale: float, rank: int, device):
     """chr1-size synthetic contig for this rank (seed differs per rank), admission-filtered and packed."""
     from decodingustools_b200 import synth
-    from decodingustools_b200.callable_loci import admit_reads, compact_reads, count_unique_reads
+    from decodingustools_b200.callable_loci import admit_reads, compact_reads
     from decodingustools_b200.options import CallableOptions
     opt = CallableOptions()
     length = max(100_000, int(synth.HG38["chr1"] * scale))
@@ -127,10 +127,13 @@ def make_workload(scale: float, rank: int, device):
     t_gen = time.time() - t0
     t0 = time.time()
     keep = admit_reads(c.reads, opt.pileup_max_depth, 0)
-    n_unique = count_unique_reads(c.reads, keep, c.length)
-    reads = compact_reads(c.reads, keep)
+    cells = int(c.reads.ref_len()[keep].sum())
+    if np.array_equal(keep, (c.reads.flag & 4) == 0):
+        reads = c.reads          # only placed-unmapped records were refused: the kernel skips FLAG 0x4 itself, no repacking needed
+    else:
+        reads = compact_reads(c.reads, keep)
     t_admit = time.time() - t0
-    return opt, c, reads, n_unique, {"synth_s": round(t_gen, 2), "host_admission_s": round(t_admit, 2)}
+    return opt, c, reads, cells, {"synth_s": round(t_gen, 2), "host_admission_s": round(t_admit, 2)}
 
 
 def oracle_sample(c, reads_unfiltered, opt, sample_bp: int):
@@ -200,32 +203,41 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    opt, c, reads, n_unique, prep = make_workload(args.scale, rank, dev)
-    cells_expected = int(reads.ref_len().sum())
+    opt, c, reads, cells_expected, prep = make_workload(args.scale, rank, dev)
     alg_bytes = reads.nbytes_device() + c.length // 8          # packed columns + 1 bit per reference base
     span = reads.max_ref_span()
 
-    # pinned host copies of the columns (the e2e leg streams from these)
-    signed = {"pos": np.int32, "flag": np.int16, "mapq": np.uint8, "cigar": np.int32, "qual": np.uint8}
-    cols = {k: torch.from_numpy(getattr(reads, k).view(dt)).pin_memory() for k, dt in signed.items()}
-    ref_pinned = torch.from_numpy(c.ref).pin_memory()
-    cig_off = reads.cigar_off.astype(np.int64); q_off = reads.qual_off.astype(np.int64)
+    # page-lock the column buffers in place (the e2e leg streams from them; no second host copy)
+    rt = torch.cuda.cudart()
+    class _Pinned:
+        def __init__(self, arr):
+            self.arr = arr
+            rc = rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        def data_ptr(self):
+            return self.arr.ctypes.data
+    cols = {k: _Pinned(getattr(reads, k)) for k in ("pos", "flag", "mapq", "cigar", "qual")}
+    ref_pinned = _Pinned(c.ref)
 
     ctx = CallableLociContext(opt, device=local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
+    cig_off = reads.cigar_off.astype(np.int64); q_off = reads.qual_off.astype(np.int64)
+    # column batches as a decoder thread would emit them: batch-relative offset columns, page-locked
+    batches = []
+    for lo in range(0, reads.n, args.batch_reads):
+        hi = min(reads.n, lo + args.batch_reads)
+        co = _Pinned(np.ascontiguousarray((cig_off[lo:hi + 1] - cig_off[lo]).astype(np.uint32)))
+        qo = _Pinned(np.ascontiguousarray((q_off[lo:hi + 1] - q_off[lo]).astype(np.uint64)))
+        batches.append((lo, hi, co, qo))
+
     def e2e_pass():
         """Public call sequence with host buffers: begin (reference upload) -> column batches -> finish (D2H)."""
         ctx._check(ctx._L.clb_begin_contig(ctx._h, 0, b"chr1", c.length, ref_pinned.data_ptr(), c.length, 0, c.length, 0, c.length, span))
         ctx.reserve(reads.n, reads.n_cigar, reads.n_qual)
-        B = args.batch_reads
-        # batch-relative offset columns are prepared per batch on the host (what a decoder thread would emit)
-        for lo in range(0, reads.n, B):
-            hi = min(reads.n, lo + B)
-            co = torch.from_numpy((cig_off[lo:hi + 1] - cig_off[lo]).astype(np.uint32).view(np.int32))
-            qo = torch.from_numpy(q_off[lo:hi + 1] - q_off[lo])
-            keepalive.append((co, qo))
+        for lo, hi, co, qo in batches:
             ctx.push_raw(hi - lo, int(cig_off[hi] - cig_off[lo]), int(q_off[hi] - q_off[lo]),
                          cols["pos"].data_ptr() + 4 * lo, cols["flag"].data_ptr() + 2 * lo, cols["mapq"].data_ptr() + lo,
                          co.data_ptr(), cols["cigar"].data_ptr() + 4 * int(cig_off[lo]), qo.data_ptr(),
@@ -284,7 +296,6 @@ def main():
     e2e_ms = []
     r = first
     for i in range(args.e2e_steps):
-        keepalive.clear()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -325,7 +336,7 @@ def main():
                          "traffic": traffic, "kernel": "k_pileup_classify", "kernel_ms": pileup_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_cell": alg_bytes / cells_expected, "peak_source": peak_src},
             "e2e": {"value": cells_all / (e2e_best * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_best,
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_best, "h2d_device_ms": round(float(r.h2d_ms), 2),
                     "note": "clb_begin_contig + clb_push_reads batches from pinned host columns + clb_finish_contig (D2H); PCIe-bound"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
