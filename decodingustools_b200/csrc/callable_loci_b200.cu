@@ -51,7 +51,7 @@ struct clb_ctx {
     uint64_t n_reads = 0, n_cigar = 0, n_qual = 0;
     long long last_pos = -1;
 
-    DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end;
+    DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end, cigar_ckpt;
     DevBuf nmask, ref_ascii;
     DevBuf stats_padded, counters, rec, win_tab, win_rlo, win_rhi, win_out, intervals, misc;
     DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state, timing;
@@ -124,6 +124,7 @@ KParams make_params(clb_ctx *c) {
     P.cigar_off = (const uint32_t *)c->cigar_off.p; P.cigar = (const uint32_t *)c->cigar.p;
     P.qual_off = (const uint64_t *)c->qual_off.p; P.qual = (const uint8_t *)c->qual.p;
     P.read_end = c->long_mode ? (const uint32_t *)c->read_end.p : nullptr;
+    P.cigar_ckpt = c->long_mode ? (const uint2 *)c->cigar_ckpt.p : nullptr;
     P.nmask = (const uint32_t *)c->nmask.p;
     P.region_start = c->region_start; P.region_end = c->region_end;
     P.min_depth = c->opt.min_depth; P.max_depth = c->opt.max_depth; P.min_depth_for_low_mapq = c->opt.min_depth_for_low_mapq;
@@ -154,11 +155,6 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
         (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (uint32_t *)ctx->win_rlo.p, (uint32_t *)ctx->win_rhi.p);
     KParams P = make_params(ctx);
     P.win_first = w0;
-    {
-        // typical segment length in 16-byte chunks (+ alignment slack), from the mean quality length of the contig so far
-        const uint64_t mean_q = ctx->n_reads ? ctx->n_qual / ctx->n_reads : 0;
-        P.pool_nc_max = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(4, (mean_q + 30) / 16 + 1));
-    }
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
     if (ctx->opt.min_base_quality >= 128) k_pileup_classify<true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
     else k_pileup_classify<false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
@@ -332,7 +328,7 @@ void clb_destroy(clb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end,
+    for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end, &ctx->cigar_ckpt,
                       &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_rlo,
                       &ctx->win_rhi, &ctx->win_out, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
         release(*b);
@@ -482,11 +478,18 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
                                                    (uint32_t)ctx->n_cigar, ctx->n_qual);
     ctx->launches += 2;
     if (r0 == 0) ctx->long_mode = b->n_cigar > 4 * b->n_reads;     // decided once per contig
-    if (ctx->long_mode || ctx->span_on_device) {
-        if (ctx->long_mode && (rc = ensure(ctx, ctx->read_end, ((size_t)r0 + n + 1) * 4, true, ctx->s_compute))) return rc;
+    if (ctx->long_mode) {
+        // read ends, maximum span and CIGAR checkpoints in one pass (one warp per read)
+        if ((rc = ensure(ctx, ctx->read_end, ((size_t)r0 + n + 1) * 4, true, ctx->s_compute))) return rc;
+        if ((rc = ensure(ctx, ctx->cigar_ckpt, ((ctx->n_cigar + b->n_cigar) / 32 + 2) * sizeof(uint2), true, ctx->s_compute))) return rc;
+        k_cigar_checkpoints<<<(n + 7) / 8, 256, 0, ctx->s_compute>>>((const int32_t *)ctx->pos.p, (const uint32_t *)ctx->cigar_off.p,
+                                                                     (const uint32_t *)ctx->cigar.p, r0, r0 + n, (uint32_t *)ctx->read_end.p,
+                                                                     ctx->span_on_device ? (uint32_t *)ctx->misc.p + M_MAXSPAN : nullptr,
+                                                                     (uint2 *)ctx->cigar_ckpt.p);
+        ctx->launches++;
+    } else if (ctx->span_on_device) {
         k_read_end<<<nb, 256, 0, ctx->s_compute>>>((const int32_t *)ctx->pos.p, (const uint32_t *)ctx->cigar_off.p, (const uint32_t *)ctx->cigar.p,
-                                                   r0, r0 + n, ctx->long_mode ? (uint32_t *)ctx->read_end.p : nullptr,
-                                                   ctx->span_on_device ? (uint32_t *)ctx->misc.p + M_MAXSPAN : nullptr);
+                                                   r0, r0 + n, nullptr, (uint32_t *)ctx->misc.p + M_MAXSPAN);
         ctx->launches++;
     }
     ctx->n_reads += n; ctx->n_cigar += b->n_cigar; ctx->n_qual += b->n_qual;

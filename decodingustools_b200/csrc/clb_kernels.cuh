@@ -66,6 +66,7 @@ struct KParams {
     const uint64_t *qual_off;
     const uint8_t  *qual;
     const uint32_t *read_end;      // optional (long-read mode): pos + reference span, else nullptr
+    const uint2    *cigar_ckpt;    // optional (long-read mode): (reference, query) offset of the owning read at every 32nd CIGAR op
     // contig / region
     const uint32_t *nmask;         // bit-packed REF_N mask, zero padded past the contig end
     uint32_t region_start, region_end;
@@ -76,7 +77,6 @@ struct KParams {
     // windows
     const uint32_t *win_rlo, *win_rhi;
     uint32_t win_first;
-    uint32_t pool_nc_max;          // segments of at most this many 16-byte chunks go to the CTA-wide pool
     // outputs
     unsigned long long *stats;     // [N_STATS * STAT_STRIDE]
     unsigned long long *bins;      // [3][n_bins]
@@ -315,6 +315,62 @@ __device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint3
     __syncwarp();
 }
 
+// Warp-collective expansion of one long CIGAR: 32 ops per step (blocks aligned to 32 ops of the contig-wide CIGAR column),
+// shuffle prefix sums over the (reference, query) lengths, one M-segment per lane streamed right away.  With checkpoints
+// (k_cigar_checkpoints) the walk starts at the last block that begins at or left of the window instead of at the read start.
+template <bool BQ_HI>
+__device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P, uint32_t sLQ_s, uint32_t slab, int crel, uint32_t cmq,
+                                                 uint32_t c0, uint32_t cn, uint32_t clq, uint64_t cq0, uint4 *myDesc, const uint32_t *sRcp,
+                                                 const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum,
+                                                 uint32_t &acc_cnt, unsigned long long &acc_mapq, int lane) {
+    const uint32_t lq_arr = sLQ_s + slab * (uint32_t)(LQ_SLAB * 4);
+    const bool cpass = cmq >= W.min_mapq;
+    const uint32_t c1 = c0 + cn;
+    uint32_t ob = c0;
+    int rp_carry = crel; uint32_t qp_carry = 0;
+    if (P.cigar_ckpt) {
+        const uint32_t g_first = (c0 >> 5) + 1u, g_last = (c1 - 1u) >> 5;      // checkpoints strictly inside this read
+        uint32_t gs = 0;
+        for (uint32_t base = g_first; base <= g_last; base += 32) {
+            const uint32_t g = base + lane;
+            const bool ok = g <= g_last;
+            const uint32_t x = ok ? P.cigar_ckpt[g].x : 0u;
+            const uint32_t bal = __ballot_sync(FULL, ok && ((long long)crel + (long long)x > 0));   // block starts right of entry 0
+            if (bal) { gs = base + (uint32_t)__ffs(bal) - 2u; break; }          // the block before the first such one
+            gs = min(g_last, base + 31u);
+        }
+        if (gs >= g_first) {
+            const uint2 ck = P.cigar_ckpt[gs];
+            ob = gs << 5;
+            rp_carry = (int)min((long long)crel + (long long)ck.x, (long long)WN);
+            qp_carry = ck.y;
+        }
+    }
+    while (ob < c1) {
+        const uint32_t bend = min(c1, (ob | 31u) + 1u);
+        const uint32_t v = (ob + lane < bend) ? P.cigar[ob + lane] : 0xfu;
+        const uint32_t op = v & 15u, len = v >> 4;
+        const uint32_t rl = ((0x18du >> op) & 1u) ? len : 0u, ql = ((0x193u >> op) & 1u) ? len : 0u;
+        unsigned long long rs = rl; uint32_t qs = ql;                 // 32 ops of < 2^28 bases each: the reference sum needs 33 bits
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const unsigned long long t1 = __shfl_up_sync(FULL, rs, dd); const uint32_t t2 = __shfl_up_sync(FULL, qs, dd);
+            if (lane >= dd) { rs += t1; qs += t2; }
+        }
+        Seg s; bool hs = false;
+        const long long my_rel = (long long)rp_carry + (long long)(rs - rl);
+        if (cpass && ((0x181u >> op) & 1u) && my_rel < (long long)WN)
+            hs = emit_m(W, lq_arr, (int)my_rel, qp_carry + (qs - ql), len, cq0, clq, s);
+        run_segments<BQ_HI>(W, sLQ_s, slab, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+        const long long nxt = (long long)rp_carry + (long long)__shfl_sync(FULL, rs, 31);
+        rp_carry = (int)min(nxt, (long long)WN);                      // saturate right of the window
+        qp_carry += __shfl_sync(FULL, qs, 31);
+        if (rp_carry >= (int)W.n_ent) break;                          // rest of the read lies right of the window
+        ob = bend;
+    }
+    if (lane == 0) emit_read(W, crel, rp_carry, cmq, acc_mapq);
+}
+
 // shared memory: A | B | LQ (KLQ packed-u8 arrays) | masks | first | desc | scan | last | warp stats | next
 constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
 #ifndef CLB_DCAP
@@ -322,8 +378,9 @@ constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
 #endif
 constexpr int DCAP = CLB_DCAP;        // CTA-wide segment pool (descriptors); a 32-read batch adds at most 64
 constexpr int BPR = DCAP / 64;        // batches per round
+constexpr int CPLX_CAP = BPR * 32;    // long-CIGAR reads queued per round for CTA-wide distribution (a round never holds more reads)
 constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 16 + 64 * 4 + NT
-                            + (size_t)NWARPS * N_STATS * 8 + 64 + (size_t)CLB_STAGE * 32 * NT;
+                            + (size_t)NWARPS * N_STATS * 8 + 128 + 2 * CPLX_CAP * 4 + (size_t)CLB_STAGE * 32 * NT;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
 static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region is zeroed with 16-byte stores");
 
@@ -347,7 +404,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w = P.win_first + blockIdx.x;
 #if CLB_STAGE > 0
-    const uint32_t sRing = smem_addr(sCtl + 16) + (uint32_t)tid * (32u * CLB_STAGE);     // this thread's staging ring (16-byte aligned)
+    const uint32_t sRing = smem_addr(sCtl + 32 + 2 * CPLX_CAP) + (uint32_t)tid * (32u * CLB_STAGE);     // this thread's staging ring (16-byte aligned)
 #endif
 #define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
     CLB_STAMP(0);
@@ -398,6 +455,8 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     for (int i = tid; i < NFIRST; i += NT) sFirst[i] = P.first_tab[i];
     for (int i = tid; i < NRCP; i += NT) sRcp[i] = i > 1 ? 0xffffffffu / (uint32_t)i + 1u : 0u;
     if (tid < 6) sCtl[tid] = 0;
+    if (tid >= 16 && tid < 20) sCtl[tid] = 0;                // [16 + 2 * parity]: queued long reads, next to expand
+    uint32_t *sCplx = sCtl + 32;                            // [parity][CPLX_CAP] read indices
     if (tid == 0) {                                          // runtime divisions once per CTA instead of once per thread
         const uint32_t nr = (n_batches + BPR - 1) / BPR;
         sCtl[8] = nr; sCtl[9] = nr ? (n_batches + nr - 1) / nr : 0u;
@@ -487,55 +546,28 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
             if (nfast) emit_read(W, rel, rp, mq, acc_mapq);
         }
         {
-            // pool append (warp-aggregated); segments longer than the pool's slot budget are streamed by this warp right away
+            // pool append (warp-aggregated)
             const uint32_t nc0 = h0 ? seg_chunks(sg0) : 0u, nc1 = h1 ? seg_chunks(sg1) : 0u;
-            const bool p0 = h0 && nc0 <= P.pool_nc_max, p1 = h1 && nc1 <= P.pool_nc_max;
-            const uint32_t bal0 = __ballot_sync(FULL, p0), bal1 = __ballot_sync(FULL, p1);
+            const uint32_t bal0 = __ballot_sync(FULL, h0), bal1 = __ballot_sync(FULL, h1);
             const uint32_t n0 = __popc(bal0), n1 = __popc(bal1);
             if (n0 + n1) {
-                const uint32_t mx = __reduce_max_sync(FULL, max(p0 ? nc0 : 0u, p1 ? nc1 : 0u));
+                const uint32_t mx = __reduce_max_sync(FULL, max(nc0, nc1));
                 uint32_t base = 0;
                 if (lane == 0) { base = atomicAdd(&ctl[1], n0 + n1); atomicMax(&ctl[2], mx); }
                 base = __shfl_sync(FULL, base, 0);
                 const uint32_t lt = (1u << lane) - 1u;
-                if (p0) sPool[base + __popc(bal0 & lt)] = make_uint4(sg0.qrel, sg0.rrel, sg0.len, nc0 | (slab << 16));
-                if (p1) sPool[base + n0 + __popc(bal1 & lt)] = make_uint4(sg1.qrel, sg1.rrel, sg1.len, nc1 | (slab << 16));
+                if (h0) sPool[base + __popc(bal0 & lt)] = make_uint4(sg0.qrel, sg0.rrel, sg0.len, nc0 | (slab << 16));
+                if (h1) sPool[base + n0 + __popc(bal1 & lt)] = make_uint4(sg1.qrel, sg1.rrel, sg1.len, nc1 | (slab << 16));
             }
-            run_segments<BQ_HI>(W, sLQ_s, slab, h0 && !p0, sg0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
-            run_segments<BQ_HI>(W, sLQ_s, slab, h1 && !p1, sg1, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
         }
 
-        // long CIGARs: the whole warp expands one read at a time with prefix sums over 32 ops
-        uint32_t cmask = __ballot_sync(FULL, cplx);
-        while (cmask) {
-            const int src = __ffs(cmask) - 1; cmask &= cmask - 1;
-            const int crel = __shfl_sync(FULL, rel, src);
-            const uint32_t cmq = __shfl_sync(FULL, mq, src), cc0 = __shfl_sync(FULL, c0, src), cn = __shfl_sync(FULL, nops, src);
-            const uint32_t clq = __shfl_sync(FULL, lq, src);
-            const uint64_t cq0 = __shfl_sync(FULL, (unsigned long long)q0, src);
-            const bool cpass = cmq >= W.min_mapq;
-            int rp_carry = crel; uint32_t qp_carry = 0;
-            for (uint32_t ob = 0; ob < cn; ob += 32) {
-                const uint32_t v = (ob + lane < cn) ? P.cigar[cc0 + ob + lane] : 0xfu;
-                const uint32_t op = v & 15u, len = v >> 4;
-                const uint32_t rl = ((0x18du >> op) & 1u) ? len : 0u, ql = ((0x193u >> op) & 1u) ? len : 0u;
-                unsigned long long rs = rl; uint32_t qs = ql;             // 32 ops of < 2^28 bases each: the reference sum needs 33 bits
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const unsigned long long t1 = __shfl_up_sync(FULL, rs, dd); const uint32_t t2 = __shfl_up_sync(FULL, qs, dd);
-                    if (lane >= dd) { rs += t1; qs += t2; }
-                }
-                Seg s; bool hs = false;
-                const long long my_rel = (long long)rp_carry + (long long)(rs - rl);
-                if (cpass && ((0x181u >> op) & 1u) && my_rel < (long long)WN)
-                    hs = emit_m(W, lq_arr, (int)my_rel, qp_carry + (qs - ql), len, cq0, clq, s);
-                run_segments<BQ_HI>(W, sLQ_s, slab, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
-                const long long nxt = (long long)rp_carry + (long long)__shfl_sync(FULL, rs, 31);
-                rp_carry = (int)min(nxt, (long long)WN);                  // saturate right of the window
-                qp_carry += __shfl_sync(FULL, qs, 31);
-                if (rp_carry >= (int)n_ent) break;                       // rest of the read lies right of the window
-            }
-            if (lane == 0) emit_read(W, crel, rp_carry, cmq, acc_mapq);
+        // long CIGARs are queued for the whole CTA and expanded after the pool streaming, one read per warp at a time
+        const uint32_t cmask = __ballot_sync(FULL, cplx);
+        if (cmask) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&sCtl[16 + 2 * (round & 1)], (uint32_t)__popc(cmask));
+            base = __shfl_sync(FULL, base, 0);
+            if (cplx) sCplx[(round & 1) * CPLX_CAP + base + __popc(cmask & ((1u << lane) - 1u))] = i0 + u * NT + lane;
         }
         }
     }
@@ -549,6 +581,22 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
 #else
         process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT);
 #endif
+        // queued long reads: warps pull one at a time (balanced no matter which groups they came from)
+        const uint32_t ncp = sCtl[16 + 2 * (round & 1)];
+        if (tid >= 2 && tid < 4) sCtl[16 + 2 * ((round + 1) & 1) + (tid - 2)] = 0u;
+        for (;;) {
+            uint32_t qi = 0;
+            if (lane == 0) qi = atomicAdd(&sCtl[17 + 2 * (round & 1)], 1u);
+            qi = __shfl_sync(FULL, qi, 0);
+            if (qi >= ncp) break;
+            const uint32_t r = sCplx[(round & 1) * CPLX_CAP + qi];
+            const uint32_t c0 = P.cigar_off[r], c1 = P.cigar_off[r + 1];
+            const uint64_t q0 = P.qual_off[r], ql = P.qual_off[r + 1] - q0;
+            const uint32_t bi = (r - r_lo) >> 5;
+            expand_long_read<BQ_HI>(W, P, sLQ_s, W.lq_packed ? bi / BPA : 0u, (int)((long long)P.pos[r] - W.wb), P.mapq[r], c0, c1 - c0,
+                                    ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql, q0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum,
+                                    acc_cnt, acc_mapq, lane);
+        }
     }
     __syncthreads();                                         // counters final / pool free for the next round
     }
@@ -796,6 +844,27 @@ __global__ void k_read_end(const int32_t *pos, const uint32_t *cigar_off, const 
     }
     span = __reduce_max_sync(FULL, span);
     if (max_span && (threadIdx.x & 31) == 0 && span) atomicMax(max_span, span);
+}
+
+// Long-read mode: one warp per read walks the CIGAR once, 32 ops per step aligned to the contig-wide CIGAR column, and
+// records the read's cumulative (reference, query) offsets at every 32-op boundary inside it, its end and the maximum span.
+__global__ void k_cigar_checkpoints(const int32_t *pos, const uint32_t *cigar_off, const uint32_t *cigar, uint32_t r0, uint32_t r1,
+                                    uint32_t *read_end, uint32_t *max_span, uint2 *ckpt) {
+    const uint32_t r = r0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= r1) return;
+    const uint32_t c0 = cigar_off[r], c1 = cigar_off[r + 1];
+    uint32_t ob = c0, cr = 0, cq = 0;
+    while (ob < c1) {
+        const uint32_t bend = min(c1, (ob | 31u) + 1u);
+        const uint32_t v = (ob + lane < bend) ? cigar[ob + lane] : 0xfu;
+        const uint32_t op = v & 15u, len = v >> 4;
+        cr += __reduce_add_sync(FULL, ((0x18du >> op) & 1u) ? len : 0u);
+        cq += __reduce_add_sync(FULL, ((0x193u >> op) & 1u) ? len : 0u);
+        ob = bend;
+        if (ob < c1 && lane == 0) ckpt[ob >> 5] = make_uint2(cr, cq);
+    }
+    if (lane == 0) { if (read_end) read_end[r] = (uint32_t)pos[r] + cr; if (max_span && cr) atomicMax(max_span, cr); }
 }
 
 // batch append, step 1: validate ordering of the freshly copied (still batch-relative) columns.
