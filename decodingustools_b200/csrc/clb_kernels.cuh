@@ -30,10 +30,7 @@ constexpr int NWARPS = NT / 32;
 #define CLB_PPT 8
 #endif
 #ifndef CLB_MINB
-#define CLB_MINB 4
-#endif
-#ifndef CLB_STAGE
-#define CLB_STAGE 0              // >0: per-thread cp.async staging ring of this many 32-byte slots for the pooled segments
+#define CLB_MINB 5
 #endif
 constexpr int PPT = CLB_PPT;          // window entries per thread in the classify phase
 constexpr int WN = NT * PPT;          // entries per window; entry 0 is the halo position (window start - 1)
@@ -104,6 +101,11 @@ __device__ __forceinline__ bool op_ref(uint32_t op) { return op == 0 || op == 2 
 __device__ __forceinline__ bool op_qry(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
 
 struct Seg { uint32_t qrel, rrel, len; };
+// 8-byte segment descriptor: x = qrel; y = rrel (11 bits) | len (11) | chunks (8) | low-BQ slab (2)
+static_assert(WN <= 2048 && KLQ <= 4, "descriptor bit fields");
+__device__ __forceinline__ uint2 pack_desc(const Seg &s, uint32_t nc, uint32_t slab) {
+    return make_uint2(s.qrel, s.rrel | (s.len << 11) | (nc << 22) | (slab << 30));
+}
 
 // Per-CTA constants; shared-memory arrays are addressed through 32-bit shared-window addresses
 struct Win {
@@ -209,12 +211,12 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
 }
 
 // Stream the qualities of the n_owner segments whose descriptors sit in desc[0..n_owner):
-//   desc = (qrel, rrel, len, n_chunks | low-BQ slab << 16).
+//   desc = pack_desc(segment, n_chunks, low-BQ slab).
 // Every segment gets S2 slots of two consecutive chunks (S2 = ceil(largest chunk count / 2)), so slot f belongs to
 // segment f / S2: no lookup table and no prefix sum; slots past a segment's end run empty.  The caller's threads
 // cover slots f0, f0 + stride, ... (a warp: f0 = lane, stride 32; the whole CTA: f0 = tid, stride NT).
 template <bool BQ_HI>
-__device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint4 *desc,
+__device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint2 *desc,
                                               const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
                                               uint32_t &acc_sum, uint32_t &acc_cnt, uint32_t f0, uint32_t stride) {
     const uint32_t total = n_owner * S2;
@@ -223,9 +225,9 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
     for (uint32_t f = f0; f < total; f += stride) {
         const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
         const uint32_t c = 2u * (f - o * S2);
-        const uint4 d = desc[o];
+        const uint2 d = desc[o];
         const uint32_t head = d.x & 15u;
-        const int rem = (int)(head + d.z) - (int)(16u * c);            // bytes from chunk c's start to the segment end
+        const int rem = (int)(head + ((d.y >> 11) & 0x7ffu)) - (int)(16u * c);   // bytes from chunk c's start to the segment end
         if (rem <= 0) continue;
         const uint4 *src = reinterpret_cast<const uint4 *>(qb + (d.x & ~15u)) + c;
 #ifdef CLB_EXPERIMENT_NOLOAD
@@ -234,82 +236,26 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
         const uint4 v0 = ldg_stream(src);
         const uint4 v1 = ldg_stream(src + 1);                             // may lie past the segment (buffers are padded): masked below
 #endif
-        const int e0 = (int)(d.y + 16u * c) - (int)head;
-        const uint32_t lq_arr = sLQ_s + (d.w >> 16) * (uint32_t)(LQ_SLAB * 4);
+        const int e0 = (int)((d.y & 0x7ffu) + 16u * c) - (int)head;
+        const uint32_t lq_arr = sLQ_s + (d.y >> 30) * (uint32_t)(LQ_SLAB * 4);
         process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
         if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
     }
 }
-
-#if CLB_STAGE > 0
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
-    return r;
-}
-
-// Same slot walk as process_slots, but every thread keeps CLB_STAGE slots (32 bytes each) in flight through its own
-// cp.async staging ring in shared memory: the copies need no registers and no barrier (a thread only waits for its own groups).
-template <bool BQ_HI>
-__device__ __forceinline__ void process_slots_staged(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint4 *desc,
-                                                     const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
-                                                     uint32_t &acc_sum, uint32_t &acc_cnt, uint32_t f0, uint32_t stride, uint32_t ring) {
-    const uint32_t total = n_owner * S2;
-    const uint32_t rcp = S2 < (uint32_t)NRCP ? sRcp[S2] : 0xffffffffu / S2 + 1u;
-    const uint8_t *qb = W.qual + W.qbase;
-    auto issue = [&](uint32_t f, uint32_t k) {
-        if (f < total) {
-            const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
-            const uint32_t c = 2u * (f - o * S2);
-            const uint4 d = desc[o];
-            if ((int)((d.x & 15u) + d.z) - (int)(16u * c) > 0) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(qb + (d.x & ~15u)) + c;
-                cp_async16(ring + 32u * k, src); cp_async16(ring + 32u * k + 16u, src + 1);
-            }
-        }
-        cp_async_commit();                                   // always: keeps the group count uniform
-    };
-#pragma unroll
-    for (int k = 0; k < CLB_STAGE; k++) issue(f0 + k * stride, k);
-    uint32_t k = 0;
-    for (uint32_t f = f0; f < total; f += stride) {
-        cp_async_wait<CLB_STAGE - 1>();
-        const uint32_t o = S2 > 1 ? __umulhi(f, rcp) : f;
-        const uint32_t c = 2u * (f - o * S2);
-        const uint4 d = desc[o];
-        const uint32_t head = d.x & 15u;
-        const int rem = (int)(head + d.z) - (int)(16u * c);
-        const uint4 v0 = lds128(ring + 32u * k), v1 = lds128(ring + 32u * k + 16u);
-        issue(f + CLB_STAGE * stride, k);
-        k = k + 1 == CLB_STAGE ? 0 : k + 1;
-        if (rem <= 0) continue;
-        const int e0 = (int)(d.y + 16u * c) - (int)head;
-        const uint32_t lq_arr = sLQ_s + (d.w >> 16) * (uint32_t)(LQ_SLAB * 4);
-        process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
-        if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
-    }
-    cp_async_wait<0>();
-}
-#endif
 
 __device__ __forceinline__ uint32_t seg_chunks(const Seg &s) { return ((s.qrel & 15u) + s.len + 15u) >> 4; }
 
 // Warp-collective: lanes holding a segment (has) publish it compactly into the warp's descriptor area and stream it
 // right away (segments too long for the CTA pool, and the long-CIGAR path).
 template <bool BQ_HI>
-__device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint32_t slab, bool has, const Seg &sg, uint4 *myDesc,
+__device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint32_t slab, bool has, const Seg &sg, uint2 *myDesc,
                                              const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
                                              uint32_t &acc_sum, uint32_t &acc_cnt, int lane) {
     const uint32_t bal = __ballot_sync(FULL, has);
     if (bal == 0) return;
     const uint32_t nc = has ? seg_chunks(sg) : 0u;
     const uint32_t S2 = (__reduce_max_sync(FULL, nc) + 1u) >> 1;
-    if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = make_uint4(sg.qrel, sg.rrel, sg.len, nc | (slab << 16));
+    if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = pack_desc(sg, nc, slab);
     __syncwarp();
     process_slots<BQ_HI>(W, sLQ_s, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)lane, 32u);
     __syncwarp();
@@ -320,7 +266,7 @@ __device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint3
 // (k_cigar_checkpoints) the walk starts at the last block that begins at or left of the window instead of at the read start.
 template <bool BQ_HI>
 __device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P, uint32_t sLQ_s, uint32_t slab, int crel, uint32_t cmq,
-                                                 uint32_t c0, uint32_t cn, uint32_t clq, uint64_t cq0, uint4 *myDesc, const uint32_t *sRcp,
+                                                 uint32_t c0, uint32_t cn, uint32_t clq, uint64_t cq0, uint2 *myDesc, const uint32_t *sRcp,
                                                  const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum,
                                                  uint32_t &acc_cnt, unsigned long long &acc_mapq, int lane) {
     const uint32_t lq_arr = sLQ_s + slab * (uint32_t)(LQ_SLAB * 4);
@@ -379,8 +325,8 @@ constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
 constexpr int DCAP = CLB_DCAP;        // CTA-wide segment pool (descriptors); a 32-read batch adds at most 64
 constexpr int BPR = DCAP / 64;        // batches per round
 constexpr int CPLX_CAP = BPR * 32;    // long-CIGAR reads queued per round for CTA-wide distribution (a round never holds more reads)
-constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 16 + 64 * 4 + NT
-                            + (size_t)NWARPS * N_STATS * 8 + 128 + 2 * CPLX_CAP * 4 + (size_t)CLB_STAGE * 32 * NT;
+constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 8 + 64 * 4 + NT
+                            + (size_t)NWARPS * N_STATS * 8 + 128 + 2 * CPLX_CAP * 4;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
 static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region is zeroed with 16-byte stores");
 
@@ -394,8 +340,8 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     uint4 *sMaskHi = sMaskLo + 17;
     uint32_t *sFirst = reinterpret_cast<uint32_t *>(sMaskHi + 17);
     uint32_t *sRcp = sFirst + NFIRST;
-    uint4 *sDesc = reinterpret_cast<uint4 *>(sRcp + NRCP);
-    uint4 *sPool = sDesc + NWARPS * 32;
+    uint2 *sDesc = reinterpret_cast<uint2 *>(sRcp + NRCP);
+    uint2 *sPool = sDesc + NWARPS * 32;
     uint32_t *sScan = reinterpret_cast<uint32_t *>(sPool + DCAP);
     uint8_t *sLast = reinterpret_cast<uint8_t *>(sScan + 64);
     unsigned long long *sWStats = reinterpret_cast<unsigned long long *>(sLast + NT);
@@ -403,9 +349,6 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t w = P.win_first + blockIdx.x;
-#if CLB_STAGE > 0
-    const uint32_t sRing = smem_addr(sCtl + 32 + 2 * CPLX_CAP) + (uint32_t)tid * (32u * CLB_STAGE);     // this thread's staging ring (16-byte aligned)
-#endif
 #define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
     CLB_STAMP(0);
 
@@ -469,7 +412,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     CLB_STAMP(1);
     // ------------------------------------------------------------------ phase A/B: reads -> counters
     const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
-    uint4 *myDesc = sDesc + warp * 32;
+    uint2 *myDesc = sDesc + warp * 32;
     const uint32_t sLQ_s = smem_addr(sLQ);
     uint32_t acc_sum = 0, acc_cnt = 0;
     unsigned long long acc_mapq = 0;
@@ -556,8 +499,8 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
                 if (lane == 0) { base = atomicAdd(&ctl[1], n0 + n1); atomicMax(&ctl[2], mx); }
                 base = __shfl_sync(FULL, base, 0);
                 const uint32_t lt = (1u << lane) - 1u;
-                if (h0) sPool[base + __popc(bal0 & lt)] = make_uint4(sg0.qrel, sg0.rrel, sg0.len, nc0 | (slab << 16));
-                if (h1) sPool[base + n0 + __popc(bal1 & lt)] = make_uint4(sg1.qrel, sg1.rrel, sg1.len, nc1 | (slab << 16));
+                if (h0) sPool[base + __popc(bal0 & lt)] = pack_desc(sg0, nc0, slab);
+                if (h1) sPool[base + n0 + __popc(bal1 & lt)] = pack_desc(sg1, nc1, slab);
             }
         }
 
@@ -576,11 +519,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     {
         const uint32_t pool_n = ctl[1], pool_s2 = (ctl[2] + 1u) >> 1;
         if (tid < 3) sCtl[3 * ((round + 1) & 1) + tid] = tid == 0 ? rb1 : 0u;     // next round's controls (nobody reads them before the barrier below)
-#if CLB_STAGE > 0
-        process_slots_staged<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT, sRing);
-#else
         process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT);
-#endif
         // queued long reads: warps pull one at a time (balanced no matter which groups they came from)
         const uint32_t ncp = sCtl[16 + 2 * (round & 1)];
         if (tid >= 2 && tid < 4) sCtl[16 + 2 * ((round + 1) & 1) + (tid - 2)] = 0u;
