@@ -50,7 +50,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int STAT_STRIDE = 16;       // one 128-byte line per global counter (u64 units)
 
 enum { ST_REF_N = 0, ST_CALLABLE = 1, ST_NO_COVERAGE = 2, ST_LOW_COVERAGE = 3, ST_EXCESSIVE = 4, ST_POOR_MAPQ = 5 };
-enum { S_COUNT0 = 0, S_COVERED = 6, S_SUMCOV = 7, S_SUMBQ = 8, S_SUMMAPQ = 9, S_QBASES = 10, S_QBASES_B = 11, N_STATS = 12 };
+enum { S_COUNT0 = 0, S_COVERED = 6, S_SUMCOV = 7, S_SUMBQ = 8, S_SUMMAPQ = 9, S_QBASES = 10, S_RESERVED = 11, N_STATS = 12 };
 enum { ERR_QUAL_SPAN = 1, ERR_REC_OVERFLOW = 2, ERR_DEPTH = 4, ERR_UNSORTED = 8, ERR_OFFSETS = 16 };
 
 struct KParams {
@@ -176,7 +176,7 @@ __device__ __forceinline__ void emit_read(const Win &W, int rel, int rel_end, ui
 // shared-memory atomics are cheaper on sm_100a (about one warp-wide ATOMS per clock per SM) than branches around them.
 template <bool BQ_HI>
 __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int e0, uint32_t lo, uint32_t hi, uint4 v, const uint4 *sMaskLo,
-                                              const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum, uint32_t &acc_cnt) {
+                                              const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum) {
     const uint4 ml = sMaskLo[lo], mh = sMaskHi[hi];       // 0xFF in bytes outside [lo, hi)
     v.x |= ml.x | mh.x; v.y |= ml.y | mh.y; v.z |= ml.z | mh.z; v.w |= ml.w | mh.w;
     const uint32_t l0 = bytes_lt<BQ_HI>(v.x, t_low), l1 = bytes_lt<BQ_HI>(v.y, t_low);        // 0x80 in every failing byte
@@ -187,9 +187,6 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
     const uint32_t sf128 = __dp4a(v.x, l0, __dp4a(v.y, l1, __dp4a(v.z, l2, __dp4a(v.w, l3, 0u))));
     const uint32_t ninv = lo + (16u - hi);
     acc_sum += tot - 255u * ninv - (sf128 >> 7);
-#ifdef CLB_COUNT_CHECK
-    acc_cnt += 16u - ninv - (__dp4a(l0, ONES, __dp4a(l1, ONES, __dp4a(l2, ONES, __dp4a(l3, ONES, 0u)))) >> 7);
-#endif
     const uint32_t f0 = l0 >> 7, f1 = l1 >> 7, f2 = l2 >> 7, f3 = l3 >> 7;                    // 1 in every failing byte
     if (W.lq_packed) {
         // four positions per 32-bit word, one byte each: shift the 16 fail flags to the entry alignment and add them
@@ -218,7 +215,7 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
 template <bool BQ_HI>
 __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint2 *desc,
                                               const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
-                                              uint32_t &acc_sum, uint32_t &acc_cnt, uint32_t f0, uint32_t stride) {
+                                              uint32_t &acc_sum, uint32_t f0, uint32_t stride) {
     const uint32_t total = n_owner * S2;
     const uint32_t rcp = S2 < (uint32_t)NRCP ? sRcp[S2] : 0xffffffffu / S2 + 1u;     // ceil(2^32 / S2): exact quotient for f < 2^32 / S2
     const uint8_t *qb = W.qual + W.qbase;
@@ -238,8 +235,8 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
 #endif
         const int e0 = (int)((d.y & 0x7ffu) + 16u * c) - (int)head;
         const uint32_t lq_arr = sLQ_s + (d.y >> 30) * (uint32_t)(LQ_SLAB * 4);
-        process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
-        if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt);
+        process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum);
+        if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum);
     }
 }
 
@@ -250,14 +247,14 @@ __device__ __forceinline__ uint32_t seg_chunks(const Seg &s) { return ((s.qrel &
 template <bool BQ_HI>
 __device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint32_t slab, bool has, const Seg &sg, uint2 *myDesc,
                                              const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
-                                             uint32_t &acc_sum, uint32_t &acc_cnt, int lane) {
+                                             uint32_t &acc_sum, int lane) {
     const uint32_t bal = __ballot_sync(FULL, has);
     if (bal == 0) return;
     const uint32_t nc = has ? seg_chunks(sg) : 0u;
     const uint32_t S2 = (__reduce_max_sync(FULL, nc) + 1u) >> 1;
     if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = pack_desc(sg, nc, slab);
     __syncwarp();
-    process_slots<BQ_HI>(W, sLQ_s, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)lane, 32u);
+    process_slots<BQ_HI>(W, sLQ_s, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)lane, 32u);
     __syncwarp();
 }
 
@@ -268,7 +265,7 @@ template <bool BQ_HI>
 __device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P, uint32_t sLQ_s, uint32_t slab, int crel, uint32_t cmq,
                                                  uint32_t c0, uint32_t cn, uint32_t clq, uint64_t cq0, uint2 *myDesc, const uint32_t *sRcp,
                                                  const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum,
-                                                 uint32_t &acc_cnt, unsigned long long &acc_mapq, int lane) {
+                                                 unsigned long long &acc_mapq, int lane) {
     const uint32_t lq_arr = sLQ_s + slab * (uint32_t)(LQ_SLAB * 4);
     const bool cpass = cmq >= W.min_mapq;
     const uint32_t c1 = c0 + cn;
@@ -307,7 +304,7 @@ __device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P,
         const long long my_rel = (long long)rp_carry + (long long)(rs - rl);
         if (cpass && ((0x181u >> op) & 1u) && my_rel < (long long)WN)
             hs = emit_m(W, lq_arr, (int)my_rel, qp_carry + (qs - ql), len, cq0, clq, s);
-        run_segments<BQ_HI>(W, sLQ_s, slab, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, lane);
+        run_segments<BQ_HI>(W, sLQ_s, slab, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, lane);
         const long long nxt = (long long)rp_carry + (long long)__shfl_sync(FULL, rs, 31);
         rp_carry = (int)min(nxt, (long long)WN);                      // saturate right of the window
         qp_carry += __shfl_sync(FULL, qs, 31);
@@ -414,7 +411,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
     uint2 *myDesc = sDesc + warp * 32;
     const uint32_t sLQ_s = smem_addr(sLQ);
-    uint32_t acc_sum = 0, acc_cnt = 0;
+    uint32_t acc_sum = 0;
     unsigned long long acc_mapq = 0;
 
     // Rounds of at most BPR batches of 32 reads: (A) walk the CIGARs, update the difference arrays and append the
@@ -519,7 +516,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     {
         const uint32_t pool_n = ctl[1], pool_s2 = (ctl[2] + 1u) >> 1;
         if (tid < 3) sCtl[3 * ((round + 1) & 1) + tid] = tid == 0 ? rb1 : 0u;     // next round's controls (nobody reads them before the barrier below)
-        process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, acc_cnt, (uint32_t)tid, (uint32_t)NT);
+        process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)tid, (uint32_t)NT);
         // queued long reads: warps pull one at a time (balanced no matter which groups they came from)
         const uint32_t ncp = sCtl[16 + 2 * (round & 1)];
         if (tid >= 2 && tid < 4) sCtl[16 + 2 * ((round + 1) & 1) + (tid - 2)] = 0u;
@@ -534,7 +531,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
             const uint32_t bi = (r - r_lo) >> 5;
             expand_long_read<BQ_HI>(W, P, sLQ_s, W.lq_packed ? bi / BPA : 0u, (int)((long long)P.pos[r] - W.wb), P.mapq[r], c0, c1 - c0,
                                     ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql, q0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum,
-                                    acc_cnt, acc_mapq, lane);
+                                    acc_mapq, lane);
         }
     }
     __syncthreads();                                         // counters final / pool free for the next round
@@ -635,12 +632,12 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     sLast[tid] = (uint8_t)((uint32_t)(stp >> (4 * (PPT - 1))) & 15u);
     // per-warp partial sums of the additive counters (plain stores, summed after the barrier: no 64-bit smem atomics)
     {
-        uint32_t v[11];
+        uint32_t v[10];
 #pragma unroll
         for (int s = 0; s < 6; s++) v[s] = (cnt_pack >> (5 * s)) & 31u;
-        v[6] = covered; v[7] = sraw; v[8] = acc_sum; v[9] = sqc; v[10] = acc_cnt;
+        v[6] = covered; v[7] = sraw; v[8] = acc_sum; v[9] = sqc;
 #pragma unroll
-        for (int i = 0; i < 11; i++) v[i] = __reduce_add_sync(FULL, v[i]);
+        for (int i = 0; i < 10; i++) v[i] = __reduce_add_sync(FULL, v[i]);
         unsigned long long mqs = acc_mapq;
 #pragma unroll
         for (int dd = 16; dd > 0; dd >>= 1) mqs += __shfl_xor_sync(FULL, mqs, dd);
@@ -648,7 +645,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
             unsigned long long *ws = sWStats + warp * N_STATS;
 #pragma unroll
             for (int s = 0; s < 6; s++) ws[S_COUNT0 + s] = v[s];
-            ws[S_COVERED] = v[6]; ws[S_SUMCOV] = v[7]; ws[S_SUMBQ] = v[8]; ws[S_QBASES] = v[9]; ws[S_QBASES_B] = v[10]; ws[S_SUMMAPQ] = mqs;
+            ws[S_COVERED] = v[6]; ws[S_SUMCOV] = v[7]; ws[S_SUMBQ] = v[8]; ws[S_QBASES] = v[9]; ws[S_RESERVED] = 0; ws[S_SUMMAPQ] = mqs;
         }
     }
     __syncthreads();

@@ -6,7 +6,8 @@ from decodingustools_b200 import synth, _lib
 from decodingustools_b200.callable_loci import CallableLociContext, admit_reads, compact_reads
 from decodingustools_b200.options import CallableOptions
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
-c = synth.synth_short("chr1", int(synth.HG38["chr1"] * scale), 1)
+mode = sys.argv[2] if len(sys.argv) > 2 else "short"
+c = synth.synth_short("chr1", int(synth.HG38["chr1"] * scale), 1) if mode == "short" else synth.synth_long("chr1", int(synth.HG38["chr1"] * scale), 1)
 reads = compact_reads(c.reads, admit_reads(c.reads, 500, 0))
 ctx = CallableLociContext(CallableOptions())
 ctx.begin_contig(0, "chr1", c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
@@ -18,7 +19,7 @@ L.clb_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c
 rc = L.clb_debug_timing(ctx._h, buf.ctypes.data_as(C.c_void_p), nmax, C.byref(n))
 assert rc == 0
 t = buf[: n.value]
-busy = t[t[:, 7] > 300]          # windows with a normal read load
+busy = t[t[:, 7] > (300 if mode == 'short' else 20)]          # windows with a normal read load
 names = ["setup", "phaseA(round0)", "phaseB+rest rounds", "C: scan+classify+stats", "C: boundaries+records", "C: bins"]
 d = np.diff(busy[:, :7], axis=1).astype(np.float64)
 tot = d.sum(axis=1)
