@@ -289,27 +289,44 @@ __device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P,
             qp_carry = ck.y;
         }
     }
+    uint32_t v = (ob + lane < min(c1, (ob | 31u) + 1u)) ? P.cigar[ob + lane] : 0xfu;
     while (ob < c1) {
         const uint32_t bend = min(c1, (ob | 31u) + 1u);
-        const uint32_t v = (ob + lane < bend) ? P.cigar[ob + lane] : 0xfu;
         const uint32_t op = v & 15u, len = v >> 4;
+        // the next block's ops are in flight while this block's qualities are streamed
+        const uint32_t nend = min(c1, bend + 32u);
+        const uint32_t vn = (bend + lane < nend) ? P.cigar[bend + lane] : 0xfu;
         const uint32_t rl = ((0x18du >> op) & 1u) ? len : 0u, ql = ((0x193u >> op) & 1u) ? len : 0u;
-        unsigned long long rs = rl; uint32_t qs = ql;                 // 32 ops of < 2^28 bases each: the reference sum needs 33 bits
+        long long ex_r, tot_r; uint32_t ex_q, tot_q;                   // exclusive prefixes of this lane, block totals
+        if (__any_sync(FULL, len >= 2048u)) {
+            unsigned long long rs = rl; uint32_t qs = ql;               // 32 ops of < 2^28 bases each: the reference sum needs 33 bits
+#pragma unroll 1
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const unsigned long long t1 = __shfl_up_sync(FULL, rs, dd); const uint32_t t2 = __shfl_up_sync(FULL, qs, dd);
+                if (lane >= dd) { rs += t1; qs += t2; }
+            }
+            ex_r = (long long)(rs - rl); ex_q = qs - ql;
+            tot_r = (long long)__shfl_sync(FULL, rs, 31); tot_q = __shfl_sync(FULL, qs, 31);
+        } else {
+            uint32_t pk = rl | (ql << 16);                              // every op < 2048 bases: both sums stay below 2^16
 #pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-            const unsigned long long t1 = __shfl_up_sync(FULL, rs, dd); const uint32_t t2 = __shfl_up_sync(FULL, qs, dd);
-            if (lane >= dd) { rs += t1; qs += t2; }
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, pk, dd);
+                if (lane >= dd) pk += t;
+            }
+            ex_r = (long long)((pk & 0xffffu) - rl); ex_q = (pk >> 16) - ql;
+            const uint32_t tot = __shfl_sync(FULL, pk, 31);
+            tot_r = (long long)(tot & 0xffffu); tot_q = tot >> 16;
         }
         Seg s; bool hs = false;
-        const long long my_rel = (long long)rp_carry + (long long)(rs - rl);
+        const long long my_rel = (long long)rp_carry + ex_r;
         if (cpass && ((0x181u >> op) & 1u) && my_rel < (long long)WN)
-            hs = emit_m(W, lq_arr, (int)my_rel, qp_carry + (qs - ql), len, cq0, clq, s);
+            hs = emit_m(W, lq_arr, (int)my_rel, qp_carry + ex_q, len, cq0, clq, s);
         run_segments<BQ_HI>(W, sLQ_s, slab, hs, s, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, lane);
-        const long long nxt = (long long)rp_carry + (long long)__shfl_sync(FULL, rs, 31);
-        rp_carry = (int)min(nxt, (long long)WN);                      // saturate right of the window
-        qp_carry += __shfl_sync(FULL, qs, 31);
+        rp_carry = (int)min((long long)rp_carry + tot_r, (long long)WN);   // saturate right of the window
+        qp_carry += tot_q;
         if (rp_carry >= (int)W.n_ent) break;                          // rest of the read lies right of the window
-        ob = bend;
+        ob = bend; v = vn;
     }
     if (lane == 0) emit_read(W, crel, rp_carry, cmq, acc_mapq);
 }

@@ -19,7 +19,8 @@ def run(tag, c, opt):
                       "Gcells_s": round(r.summed_coverage / best / 1e6, 1), "GBps": round(byts / best / 1e6, 1), "frac": round(byts / best / 1e6 / 6537, 4)}))
     ctx.close()
 
-run("5: long reads 15kb indel-heavy, 25 Mbp", synth.synth_long("chr1", 25_000_000, 5), CallableOptions())
-run("4: 2000x chrY-size/20 (cap 500)", synth.synth_short("chrY", 2_800_000, 4, depth=2000.0), CallableOptions())
-run("4b: 2000x, --max-depth 4000 (no cap)", synth.synth_short("chrY", 1_000_000, 4, depth=2000.0), CallableOptions(max_depth=4000))
-run("1: chr22-size 30x", synth.synth_short("chr22", synth.HG38["chr22"], 1), CallableOptions())
+if __name__ == "__main__":
+  run("5: long reads 15kb indel-heavy, 25 Mbp", synth.synth_long("chr1", 25_000_000, 5), CallableOptions())
+  run("4: 2000x chrY-size/20 (cap 500)", synth.synth_short("chrY", 2_800_000, 4, depth=2000.0), CallableOptions())
+  run("4b: 2000x, --max-depth 4000 (no cap)", synth.synth_short("chrY", 1_000_000, 4, depth=2000.0), CallableOptions(max_depth=4000))
+  run("1: chr22-size 30x", synth.synth_short("chr22", synth.HG38["chr22"], 1), CallableOptions())
