@@ -1,6 +1,6 @@
 // coverage_cli.cpp -- `decodingus-tools-b200 coverage`: the reference's `coverage` command on the B200 path.
 //
-// Host side of the drop-in (SURVEY.md section 8(f), rows N1/N2/N4-partial), written in C++ because this image has no
+// Host side of the drop-in (SURVEY.md section 8(f), rows N1-N4), written in C++ because this image has no
 // Rust toolchain; it only talks to the device through the C ABI of include/callable_loci_b200.h, exactly as a Rust
 // host would.  Mirrors, with citations into /root/reference:
 //   flags and defaults                     src/cli.rs:14-61
@@ -10,11 +10,13 @@
 //   get_quality_stats                      src/callable_loci/profilers/contig_profiler.rs:123-158
 //   summary.json (written in the CWD)      src/main.rs:67-69, src/export/formats/coverage.rs (field order)
 //   detect_aligner / reference build       src/callable_loci/mod.rs:149-177, src/types.rs:100-147
-//   BamStats read length (first 10 000)    src/callable_loci/profilers/bam_stats.rs:60-76,187-193
+//   BamStats sampler, platform inference, SVG plots, HTML report: report_writer.hpp (citations there)
 // What rust-htslib did (BGZF inflate, BAM record decode, faidx) is done here: multi-threaded zlib inflate of BGZF blocks,
 // a sequential record scan (the file is coordinate sorted, so no .bai is needed) and an in-memory FASTA contig load.
-// Not produced: the HTML report and the SVG plots (rows N2-HTML/N3), sequencing-platform inference (N4) -> "Unknown".
+// The HTML page is wrapped in this tool's own header/footer unless --report-templates points at a reference checkout's
+// src/callable_loci/templates (then the page is what the reference writes, byte for byte).
 #include "../../../include/callable_loci_b200.h"
+#include "report_writer.hpp"
 
 #include <zlib.h>
 
@@ -284,7 +286,7 @@ uint64_t count_unique_names(const Columns &c, const std::vector<uint8_t> &keep, 
 }
 
 struct Options {
-    std::string bam, reference, out_bed = "callable_regions.bed", summary = "summary.html";
+    std::string bam, reference, out_bed = "callable_regions.bed", summary = "summary.html", templates;
     std::vector<std::string> contigs; bool have_contigs = false;
     clb_options o{4, 500, 10, 10, 20, 1, 0, 0.1};
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
@@ -294,7 +296,8 @@ struct Options {
 void usage() {
     fprintf(stderr, "Usage: decodingus-tools-b200 coverage <BAM_FILE> -r <REFERENCE> [-o callable_regions.bed] [-s summary.html] [-L contig]...\n"
                     "       [--min-depth 4] [--max-depth 500] [--min-mapping-quality 10] [--min-base-quality 20]\n"
-                    "       [--min-depth-for-low-mapq 10] [--max-low-mapq 1] [--max-low-mapq-fraction 0.1] [--threads N] [--device D]\n");
+                    "       [--min-depth-for-low-mapq 10] [--max-low-mapq 1] [--max-low-mapq-fraction 0.1] [--threads N] [--device D]\n"
+                    "       [--report-templates DIR]\n");
     exit(2);
 }
 
@@ -319,6 +322,7 @@ int main(int argc, char **argv) {
         else if (a == "--max-low-mapq-fraction") opt.o.max_low_mapq_fraction = std::stod(val());
         else if (a == "--threads") opt.threads = (unsigned)std::stoul(val());
         else if (a == "--device") opt.device = std::stoi(val());
+        else if (a == "--report-templates") opt.templates = val();
         else if (!a.empty() && a[0] != '-' && opt.bam.empty()) opt.bam = a;
         else usage();
     }
@@ -351,7 +355,13 @@ int main(int argc, char **argv) {
     auto check = [&](int rc, const char *what) { if (rc != 0) die(std::string("Error processing contig: ") + what + ": " + clb_last_error(ctx)); };
 
     // BamStats: first 10 000 records, primary alignments only (bam_stats.rs:60-76)
-    uint64_t bs_seen = 0, bs_reads = 0, bs_len = 0;
+    report::BamStats bs;
+    auto sample = [&](const BamRecordView &r) {
+        if (!bs.full()) bs.add_record(std::string(r.qname, r.l_qname ? r.l_qname - 1 : 0), r.flag, (uint64_t)std::max(0, r.l_seq));
+    };
+    // coverage plots land next to the BED file (callable_profiler.rs:24-27,80-83)
+    const size_t slash = opt.out_bed.find_last_of('/');
+    const std::string out_dir = slash == std::string::npos ? "" : opt.out_bed.substr(0, slash + 1);
 
     Columns cols; BamRecordView rec; bool have = bam.next(rec);
     const uint32_t maxcnt = opt.o.max_depth > 0 ? opt.o.max_depth : 500;
@@ -359,11 +369,11 @@ int main(int argc, char **argv) {
         const int32_t tid = kv.first; ContigStats &st = kv.second;
         cols.clear();
         while (have && (rec.tid < tid && rec.tid >= 0)) {               // records of contigs that were not selected
-            if (bs_seen++ < 10000 && !(rec.flag & 0x900)) { bs_reads++; bs_len += (uint64_t)std::max(0, rec.l_seq); }
+            sample(rec);
             have = bam.next(rec);
         }
         while (have && rec.tid == tid) {
-            if (bs_seen++ < 10000 && !(rec.flag & 0x900)) { bs_reads++; bs_len += (uint64_t)std::max(0, rec.l_seq); }
+            sample(rec);
             cols.push(rec);
             have = bam.next(rec);
         }
@@ -390,12 +400,20 @@ int main(int argc, char **argv) {
         st.n_covered = res.n_covered_bases; st.sum_cov = res.summed_coverage; st.sum_bq = res.summed_baseq;
         st.sum_mapq = res.summed_mapq; st.qbases = res.quality_bases;
         std::vector<uint32_t> bins(res.bins, res.bins + 3 * (size_t)res.n_bins);
-        if (clb_bed_writer_add_contig(bed, st.name.c_str(), clen, res.intervals, res.n_intervals, bins.data(), res.n_bins, res.stride, nullptr) != 0)
+        int has_bins = 0;
+        if (clb_bed_writer_add_contig(bed, st.name.c_str(), clen, res.intervals, res.n_intervals, bins.data(), res.n_bins, res.stride, &has_bins) != 0)
             die("Error processing contig: interval list does not tile the contig");
+        if (has_bins && res.stride) {                                        // finish_contig, callable_profiler.rs:64-86
+            const std::string svg = report::render_coverage_svg(st.name, clen, res.stride, bins.data(), res.n_bins);
+            const std::string path = out_dir + st.name + "_coverage.svg";
+            FILE *fs = fopen(path.c_str(), "wb");
+            if (!fs) die("Error processing contig: cannot create " + path);
+            fwrite(svg.data(), 1, svg.size(), fs); fclose(fs);
+        }
         fprintf(stderr, "%s: %llu admitted reads, %llu cells, %.2f ms on device\n", st.name.c_str(), (unsigned long long)adm.n_reads,
                 (unsigned long long)res.summed_coverage, res.kernel_ms);
     }
-    while (have && bs_seen < 10000) { if (!(rec.flag & 0x900)) { bs_reads++; bs_len += (uint64_t)std::max(0, rec.l_seq); } bs_seen++; have = bam.next(rec); }
+    while (have && !bs.full()) { sample(rec); have = bam.next(rec); }
     if (clb_bed_writer_close(bed) != 0) die("failed to write " + opt.out_bed);
     clb_destroy(ctx);
 
@@ -406,6 +424,8 @@ int main(int argc, char **argv) {
     uint64_t total_bases = 0, callable = 0, q30_bases = 0, total_qpos = 0, total_unique = 0;
     double total_depth = 0, total_mapq = 0, total_baseq = 0;
     std::string cj;
+    std::vector<report::ContigRow> rows;
+    auto exists = [](const std::string &p) { FILE *f = fopen(p.c_str(), "rb"); if (f) fclose(f); return f != nullptr; };
     for (size_t i = 0; i < order.size(); i++) {
         const ContigStats &s = *order[i];
         const double amq = s.qbases ? (double)s.sum_mapq / (double)s.qbases : 0.0, abq = s.qbases ? (double)s.sum_bq / (double)s.qbases : 0.0;
@@ -415,6 +435,10 @@ int main(int argc, char **argv) {
         total_bases += s.length; callable += s.counts[CLB_CALLABLE];
         total_depth += adep * (double)s.length; total_mapq += amq * (double)s.length; total_baseq += abq * (double)s.length;
         q30_bases += (uint64_t)(q30 / 100.0 * (double)s.length); total_qpos += s.length; total_unique += (uint32_t)s.n_reads;
+        report::ContigRow row{s.name, s.length, s.n_reads, s.n_covered, covp, adep, amq, abq, q30, {0, 0, 0, 0, 0, 0},
+                              exists(s.name + "_coverage.svg")};   // path relative to the CWD, as report.rs:318-319 tests it
+        for (int k = 0; k < 6; k++) row.counts[k] = s.counts[k];
+        rows.push_back(row);
         cj += std::string(i ? ",\n" : "") + "      {\n        \"name\": " + jstr(s.name) + ",\n        \"length\": " + std::to_string(s.length) +
               ",\n        \"unique_reads\": " + std::to_string(s.n_reads) + ",\n        \"coverage_percent\": " + fmt_f64(covp) +
               ",\n        \"average_depth\": " + fmt_f64(adep) + ",\n        \"covered_bases\": " + std::to_string(s.n_covered) +
@@ -427,17 +451,36 @@ int main(int argc, char **argv) {
     }
     const double avg_depth = total_bases ? total_depth / (double)total_bases : 0.0;
     const double call_pct = total_bases ? ((double)callable / (double)total_bases) * 100.0 : 0.0;
+    // collect_coverage_plots (api/coverage.rs:262-275): plots found in the CWD; the reference lists them in HashMap order, here by tid
+    std::string plots;
+    for (auto &kv : stats) {
+        const std::string p = kv.second.name + "_coverage.svg";
+        if (exists(p)) plots += std::string(plots.empty() ? "\n      " : ",\n      ") + jstr(p);
+    }
+    if (!plots.empty()) plots += "\n    ";
     std::string js = "{\n  \"export\": {\n    \"summary\": {\n      \"aligner\": " + jstr(detect_aligner(H.text)) + ",\n      \"reference_build\": " +
-        jstr(reference_build(H.text)) + ",\n      \"sequencing_platform\": \"Unknown\",\n      \"read_length\": " + std::to_string(bs_reads ? bs_len / bs_reads : 0) +
+        jstr(reference_build(H.text)) + ",\n      \"sequencing_platform\": " + jstr(bs.infer_platform()) + ",\n      \"read_length\": " + std::to_string(bs.average_read_length()) +
         ",\n      \"total_bases\": " + std::to_string(total_bases) + ",\n      \"callable_bases\": " + std::to_string(callable) +
         ",\n      \"callable_percentage\": " + fmt_f64(call_pct) + ",\n      \"average_depth\": " + fmt_f64(avg_depth) + ",\n      \"contigs_analyzed\": " +
         std::to_string(stats.size()) + "\n    },\n    \"contigs\": [" + (order.empty() ? "" : "\n" + cj + "\n    ") + "],\n    \"quality_metrics\": {\n      \"average_mapq\": " +
         fmt_f64(total_qpos ? total_mapq / (double)total_qpos : 0.0) + ",\n      \"average_baseq\": " + fmt_f64(total_qpos ? total_baseq / (double)total_qpos : 0.0) +
         ",\n      \"q30_percentage\": " + fmt_f64(total_qpos ? ((double)q30_bases / (double)total_qpos) * 100.0 : 0.0) + "\n    },\n    \"total_unique_reads\": " +
         std::to_string(total_unique) + "\n  },\n  \"files\": {\n    \"bed_file\": " + jstr(opt.out_bed) + ",\n    \"summary_html\": " + jstr(opt.summary) +
-        ",\n    \"coverage_plots\": []\n  }\n}";
+        ",\n    \"coverage_plots\": [" + plots + "]\n  }\n}";
     FILE *fj = fopen("summary.json", "wb");                                  // main.rs:68: always in the CWD
     if (!fj) die("cannot create summary.json");
     fwrite(js.data(), 1, js.size(), fj); fclose(fj);
+
+    // write_html_report (report.rs:136-160)
+    auto slurp = [](const std::string &p) { std::ifstream f(p, std::ios::binary); if (!f) die("cannot read " + p); return std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>()); };
+    const std::string header = opt.templates.empty() ? report::default_header() : slurp(opt.templates + "/report_header.html");
+    const std::string footer = opt.templates.empty() ? report::default_footer() : slurp(opt.templates + "/report_footer.html");
+    report::Summary sm{reference_build(H.text), detect_aligner(H.text), bs.infer_platform(), bs.average_read_length(), total_unique, total_bases, callable,
+                       (uint64_t)stats.size(), bs.max_samples, call_pct, avg_depth, total_qpos ? total_mapq / (double)total_qpos : 0.0,
+                       total_qpos ? total_baseq / (double)total_qpos : 0.0};
+    const std::string html = report::render_html_report(sm, rows, header, footer);
+    FILE *fh = fopen(opt.summary.c_str(), "wb");
+    if (!fh) die("cannot create " + opt.summary);
+    fwrite(html.data(), 1, html.size(), fh); fclose(fh);
     return 0;
 }

@@ -91,3 +91,177 @@ def build_coverage_export(contig_stats: Dict[int, ContigProfiler], counter: Call
               average_baseq=total_baseq / total_qpos if total_qpos > 0 else 0.0,
               q30_percentage=(q30_bases / total_qpos) * 100.0 if total_qpos > 0 else 0.0)
     return dict(summary=summary, contigs=contigs, quality_metrics=qm, total_unique_reads=total_unique)
+
+
+# ------------------------------------------------------------------------------------------------ coverage plot (SVG)
+def _xml_attr(v) -> str:
+    s = str(v)
+    return s.replace("&", "&amp;").replace("'", "&apos;").replace('"', "&quot;").replace("<", "&lt;").replace(">", "&gt;")
+
+
+def _tag(name: str, attrs, self_closing: bool) -> str:
+    """histogram_plotter.rs:34-48.  The reference renders its attributes in HashMap order (different from run to run);
+    here they come out in the order the reference code sets them."""
+    body = " ".join(f'{k}="{_xml_attr(v)}"' for k, v in attrs)
+    return f"<{name} {body}/>" if self_closing else f"<{name} {body}>"
+
+
+def _u32(v: int) -> int:
+    return v & 0xFFFFFFFF
+
+
+def _bar_height(count: int, stride: int, histogram_height: int) -> int:
+    import numpy as np
+    h = np.float32(count) / np.float32(stride) * np.float32(histogram_height)      # f32 arithmetic, `as u32` truncates
+    return int(h) if h > 0 else 0
+
+
+def render_coverage_svg(contig_name: str, contig_length: int, stride: int, bins) -> str:
+    """The per-contig coverage plot (histogram_plotter.rs:104-410) from the [3][n_bins] bins the device returned
+    (rows: CALLABLE, POOR_MAPPING_QUALITY, REF_N; quirk Q2 already added by the BED writer)."""
+    callable_d, lowq_d, refn_d = bins[0], bins[1], bins[2]
+    svg_width = contig_length // stride
+    histogram_height, notch = 100, 10
+    header_h = 30 + 15 + 25 + 10
+    total_h = header_h + histogram_height + 50
+    out = ['<?xml version="1.0" encoding="UTF-8" standalone="no"?>\n']
+    out.append(_tag("svg", [("xmlns", "http://www.w3.org/2000/svg"), ("width", svg_width), ("height", total_h),
+                            ("style", "background:#%06x" % 0xFFFFFF)], False) + "\n")
+    out.append(_tag("text", [("x", svg_width // 2), ("y", 20), ("text-anchor", "middle"), ("font-family", "Arial"), ("font-size", "16"),
+                             ("font-weight", "bold"), ("fill", "#000000")], False) + contig_name + "</text>\n")
+    out.append(_tag("line", [("x1", 0), ("y1", header_h - 5), ("x2", svg_width), ("y2", header_h - 5), ("stroke", "#808080"),
+                             ("stroke-width", 1)], True) + "\n")
+    out.append(_tag("rect", [("x", 0), ("y", 0), ("width", svg_width), ("height", header_h - 10), ("fill", "#F8F8F8"), ("opacity", "0.8")], True) + "\n")
+    label_y = 30 + 15 + 25 - 5
+    for pos in range(0, contig_length + 1, 10_000_000):
+        x = pos // stride
+        if x >= svg_width:
+            continue
+        if 20 <= x <= svg_width - 20:
+            out.append(_tag("text", [("x", x), ("y", label_y), ("text-anchor", "middle"), ("font-family", "Arial"), ("font-size", "16"),
+                                     ("font-weight", "bold"), ("fill", "#800080")], False) + f"{pos // 1_000_000}Mb</text>\n")
+        out.append(_tag("line", [("x1", x), ("y1", header_h), ("x2", x), ("y2", header_h + notch), ("stroke", "#800080"), ("stroke-width", 2)], True) + "\n")
+        out.append(_tag("line", [("x1", x), ("y1", header_h + histogram_height - notch), ("x2", x), ("y2", header_h + histogram_height),
+                                 ("stroke", "#800080"), ("stroke-width", 2)], True) + "\n")
+    for x in range(0, contig_length, stride):
+        idx = x // stride
+        if refn_d[idx] > 0:
+            out.append(_tag("rect", [("x", idx), ("y", header_h), ("width", 1), ("height", histogram_height), ("fill", "#000000")], True) + "\n")
+            continue
+        ch = _bar_height(int(callable_d[idx]), stride, histogram_height) if callable_d[idx] > 0 else 0
+        if callable_d[idx] > 0:
+            out.append(_tag("rect", [("x", idx), ("y", _u32(header_h + histogram_height - ch)), ("width", 1), ("height", ch), ("fill", "#007700")], True) + "\n")
+        if lowq_d[idx] > 0:
+            lh = _bar_height(int(lowq_d[idx]), stride, histogram_height)
+            out.append(_tag("rect", [("x", idx), ("y", _u32(header_h + histogram_height - lh - ch)), ("width", 1), ("height", lh), ("fill", "#770000")], True) + "\n")
+    legend_y = header_h + histogram_height + 10
+    lx = _u32(svg_width - 300) // 2                     # wraps for plots narrower than the legend, as the release build does
+    out.append("<defs>\n")
+    for gid, c0, c1 in (("callableGradient", "#007700", "#00aa00"), ("lowQualGradient", "#770000", "#aa0000")):
+        out.append(_tag("linearGradient", [("id", gid), ("x1", "0%"), ("y1", "0%"), ("x2", "100%"), ("y2", "0%"), ("fill", f"url(#{gid})")], False))
+        out.append(f'<stop offset="0%" style="stop-color:{c0};stop-opacity:0.8"/>\n')
+        out.append(f'<stop offset="100%" style="stop-color:{c1};stop-opacity:0.8"/>\n')
+        out.append("</linearGradient>\n")
+    out.append("</defs>\n")
+    for dx, fill, label in ((0, "url(#callableGradient)", "Callable Coverage"), (150, "url(#lowQualGradient)", "Low Quality Coverage"),
+                            (300, "#000000", "Reference N")):
+        out.append(_tag("rect", [("x", _u32(lx + dx)), ("y", legend_y), ("width", 20), ("height", 10), ("fill", fill)], True))
+        out.append(_tag("text", [("x", _u32(lx + dx + 25)), ("y", legend_y + 8), ("font-family", "Arial"), ("font-size", "12"), ("fill", "#000000")], False))
+        out.append(label + "</text>\n")
+    out.append("</svg>\n")
+    return "".join(out)
+
+
+# ------------------------------------------------------------------------------------------------ HTML report
+# The reference wraps the generated sections in two static template files (templates/report_header.html and
+# report_footer.html, include_str!-ed at report.rs:145,154).  They are page furniture, not output of the analysis; this
+# package ships its own minimal ones and takes the reference's through `header_html` / `footer_html` when a byte-identical
+# page is wanted.
+DEFAULT_REPORT_HEADER = """<!DOCTYPE html>
+<html lang="en">
+<head>
+<meta charset="UTF-8">
+<title>BAM Analysis Report</title>
+<style>
+body { font-family: sans-serif; margin: 2rem; }
+.stats-columns { display: flex; gap: 3rem; }
+dt { font-weight: bold; } dd { margin: 0 0 .5rem 0; }
+table { border-collapse: collapse; } td, th { border: 1px solid #ccc; padding: .3rem .6rem; text-align: left; }
+.tab-panel { display: none; } .tab-panel.active { display: block; }
+.sample-note { font-size: .7em; font-weight: normal; color: #666; }
+</style>
+</head>
+<body>
+<main>
+<h1>BAM Analysis Report</h1>
+"""
+DEFAULT_REPORT_FOOTER = """<script>
+function switchToContig(id) {
+  for (const p of document.querySelectorAll('.tab-panel')) { p.classList.remove('active'); p.style.display = 'none'; }
+  const s = document.getElementById(id);
+  if (s) { s.classList.add('active'); s.style.display = 'block'; }
+}
+document.addEventListener('DOMContentLoaded', function () {
+  const sel = document.getElementById('contig-select');
+  if (sel) switchToContig(sel.value);
+});
+</script>
+</main>
+</body>
+</html>"""
+
+
+def _row(label: str, value) -> str:
+    return f"<tr><td>{label}</td><td>{value}</td></tr>"
+
+
+def render_html_report(export: dict, max_samples: int = 10000, header_html: str | None = None, footer_html: str | None = None,
+                       plot_exists=None) -> str:
+    """report.rs:136-335 (write_html_report): BAM statistics box + one panel per contig in natural order.
+    plot_exists(path) decides whether a panel links "<contig>_coverage.svg" (the reference tests the path relative to the
+    working directory, report.rs:318-319); default os.path.exists."""
+    import os
+    plot_exists = plot_exists or os.path.exists
+    s, qm = export["summary"], export["quality_metrics"]
+    h = [DEFAULT_REPORT_HEADER if header_html is None else header_html]
+    h.append("<section class='stats-box'>")
+    h.append(f"<h2>BAM Statistics <span class='sample-note'>(based on first {max_samples} reads)</span></h2>")
+    h.append("<div class='stats-columns'><dl>")
+    pad = "\n            "
+    h.append(f"<dt>Reference Build</dt><dd>{s['reference_build']}</dd>{pad}<dt>Aligner</dt><dd>{s['aligner']}</dd>{pad}"
+             f"<dt>Sequencing Platform</dt><dd>{s['sequencing_platform']}</dd>{pad}<dt>Average read length</dt><dd>{s['read_length']} bp</dd>{pad}"
+             f"<dt>Total Unique Reads</dt><dd>{export['total_unique_reads']}</dd>{pad}<dt>Total Bases</dt><dd>{s['total_bases']}</dd>{pad}")
+    h.append("</dl><dl>")
+    h.append(f"<dt>Callable Bases</dt><dd>{s['callable_bases']}</dd>{pad}<dt>Callable Percentage</dt><dd>{s['callable_percentage']:.2f}%</dd>{pad}"
+             f"<dt>Average Depth</dt><dd>{s['average_depth']:.2f}×</dd>{pad}<dt>Contigs Analyzed</dt><dd>{s['contigs_analyzed']}</dd>{pad}"
+             f"<dt>Average MapQ</dt><dd>{qm['average_mapq']:.1f}</dd>{pad}<dt>Average BaseQ</dt><dd>{qm['average_baseq']:.1f}</dd>")
+    h.append("</dl></div></section>")
+    h.append('<div class="contig-analysis">')
+    h.append('<div class="contig-selector">\n        <select id="contig-select" onchange="switchToContig(this.value)" aria-label="Select contig">')
+    for i, c in enumerate(export["contigs"]):
+        h.append(f'<option value="panel-{i}" {"selected" if i == 0 else ""}>{c["name"]}</option>')
+    h.append("</select></div>")
+    h.append('<div class="contig-panels">')
+    section = '<tr><td colspan="2" style="font-weight: bold; background-color: #f5f5f5;">%s</td></tr>'
+    for i, c in enumerate(export["contigs"]):
+        q, d = c["quality_stats"], c["state_distribution"]
+        h.append(f'<div class="tab-panel {"active" if i == 0 else ""}" id="panel-{i}">')
+        h.append("<table><thead><tr><th>Metric</th><th>Value</th></tr></thead><tbody>")
+        h.append(_row("Length", f"{c['length']} bp") + _row("Unique Reads", c["unique_reads"]) + _row("Covered Bases", c["covered_bases"]) +
+                 _row("Coverage Percent", f"{c['coverage_percent']:.2f}%") + _row("Average Depth", f"{c['average_depth']:.2f}×"))
+        h.append(section % "Quality Metrics")
+        h.append(_row("Average MapQ", f"{q['average_mapq']:.1f}") + _row("Average BaseQ", f"{q['average_baseq']:.1f}") +
+                 _row("Q30 Percentage", f"{q['q30_percentage']:.2f}%"))
+        h.append(section % "State Distribution")
+        h.append(_row("Reference N", d["ref_n"]) + _row("Callable", d["callable"]) + _row("No Coverage", d["no_coverage"]) +
+                 _row("Low Coverage", d["low_coverage"]) + _row("Excessive Coverage", d["excessive_coverage"]) +
+                 _row("Poor Mapping Quality", d["poor_mapping_quality"]))
+        h.append("</tbody></table>")
+        plot = f"{c['name']}_coverage.svg"
+        if plot_exists(plot):
+            h.append(f'<figure class=\'coverage-plot\'>\n                <img src="{plot}" alt="Coverage distribution for {c["name"]}" loading="lazy">\n'
+                     f'                <figcaption>Coverage distribution for {c["name"]}</figcaption>\n            </figure>')
+        h.append("</div>")
+    h.append("</div></div>")
+    h.append(DEFAULT_REPORT_FOOTER if footer_html is None else footer_html)
+    return "".join(h)

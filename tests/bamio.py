@@ -25,8 +25,13 @@ def write_bgzf(path: str, payload: bytes, block: int = 0xFF00):
         f.write(_bgzf_block(b""))                # EOF marker
 
 
-def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN:bwa\n"):
-    """contigs: list of (name, length, ReadColumns) in tid order; QNAMEs are synthesised from name_id (mates share)."""
+def default_qname(contig: str, name_id: int) -> str:
+    return f"{contig}:q{name_id}"
+
+
+def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN:bwa\n", qname_fn=default_qname):
+    """contigs: list of (name, length, ReadColumns) in tid order; QNAMEs are synthesised from name_id (mates share)
+    through qname_fn(contig, name_id)."""
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l, _ in contigs) + header_extra
     out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs)))
     for n, l, _ in contigs:
@@ -34,7 +39,7 @@ def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN
         out += struct.pack("<i", len(nb)) + nb + struct.pack("<i", l)
     for tid, (name, _, rc) in enumerate(contigs):
         for i in range(rc.n):
-            qn = f"{name}:q{int(rc.name_id[i]) if rc.name_id is not None else i}".encode() + b"\0"
+            qn = qname_fn(name, int(rc.name_id[i]) if rc.name_id is not None else i).encode() + b"\0"
             c0, c1 = int(rc.cigar_off[i]), int(rc.cigar_off[i + 1])
             q0, q1 = int(rc.qual_off[i]), int(rc.qual_off[i + 1])
             lseq = q1 - q0

@@ -1,5 +1,5 @@
-"""The C++ `coverage` command (rows N1/N2): real BAM + FASTA files in, callable_regions.bed + summary.json out,
-compared with the oracle run on the same records."""
+"""The C++ `coverage` command (rows N1-N4): real BAM + FASTA files in, callable_regions.bed + summary.json + summary.html +
+SVG plots out, compared with the oracle run on the same records."""
 import json
 import os
 import subprocess
@@ -84,3 +84,33 @@ def test_cli_errors_like_the_reference(tmp_path):
     bamio.write_bam(bam, [(c.name, c.length, c.reads)]); bamio.write_fasta(fa, [(c.name, c.ref)])
     p = subprocess.run([CLI, "coverage", bam, "-r", fa, "-L", "chrZ"], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode != 0 and "None of the specified contigs (chrZ) were found in the BAM file" in p.stderr
+
+
+def test_cli_report_outputs_match_the_python_mirror(tmp_path):
+    """Rows N2-N4: SVG plots from the device bins, HTML page, platform inference -- C++ (report_writer.hpp) against the
+    Python mirror (report.py / bam_stats.py) fed with the ORACLE's bins and the JSON the CLI wrote."""
+    from decodingustools_b200 import report
+    cs = [synth.synth_short("chr1", 90_000, seed=51), synth.synth_short("chr2", 40_000, seed=52), synth.synth_short("chrM", 16_569, seed=53, depth=200.0)]
+    contigs = [(c.name, tid, c.length, c.ref, c.reads) for tid, c in enumerate(cs)]
+    bam = str(tmp_path / "in.bam"); fa = str(tmp_path / "ref.fa")
+    bamio.write_bam(bam, [(n, l, r) for n, _, l, _, r in contigs], qname_fn=lambda contig, i: f"A00123:7:HFLOWCELLX:1:1101:{contig}:{i}")
+    bamio.write_fasta(fa, [(n, ref) for n, _, _, ref, _ in contigs])
+    tdir = tmp_path / "tpl"; tdir.mkdir()
+    (tdir / "report_header.html").write_text("<html><!-- custom header -->\n"); (tdir / "report_footer.html").write_text("<!-- custom footer --></html>")
+    for extra, head, foot in (([], report.DEFAULT_REPORT_HEADER, report.DEFAULT_REPORT_FOOTER),
+                              (["--report-templates", str(tdir)], "<html><!-- custom header -->\n", "<!-- custom footer --></html>")):
+        p = subprocess.run([CLI, "coverage", bam, "-r", fa, "-o", "out.bed", *extra], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr
+        js = json.load(open(tmp_path / "summary.json"))
+        o = run_oracle(contigs, CallableOptions())
+        assert open(tmp_path / "out.bed", "rb").read() == o.bed()
+        for oc in o.contigs:
+            path = tmp_path / f"{oc.name}_coverage.svg"
+            assert path.exists() == (oc.bins is not None)
+            if oc.bins is not None:
+                assert path.read_text() == report.render_coverage_svg(oc.name, oc.length, oc.stride, oc.bins), oc.name
+        assert js["export"]["summary"]["sequencing_platform"] == "NovaSeq" and js["export"]["summary"]["read_length"] == 150
+        assert js["files"]["coverage_plots"] == [f"{oc.name}_coverage.svg" for oc in o.contigs if oc.bins is not None]
+        html = (tmp_path / "summary.html").read_text()
+        assert html == report.render_html_report(js["export"], header_html=head, footer_html=foot, plot_exists=lambda q: (tmp_path / q).exists())
+        assert html.count("<figure") == sum(oc.bins is not None for oc in o.contigs) > 0
