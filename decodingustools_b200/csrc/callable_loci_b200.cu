@@ -53,7 +53,7 @@ struct clb_ctx {
 
     DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end, cigar_ckpt;
     DevBuf nmask, ref_ascii;
-    DevBuf stats_padded, counters, rec, win_tab, win_rlo, win_rhi, win_out, intervals, misc;
+    DevBuf stats_padded, counters, rec, win_tab, win_rlo, win_rhi, win_out, deep_list, intervals, misc;
     DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state, timing;
     uint32_t rec_cap = 0;
     bool dbg = false;
@@ -70,7 +70,7 @@ struct clb_ctx {
 };
 
 // misc layout (uint32): [0] record cursor, [1] error bits, [2] n_total intervals, [3] max ref span
-enum { M_CURSOR = 0, M_ERR = 1, M_NTOTAL = 2, M_MAXSPAN = 3, M_WORDS = 8 };
+enum { M_CURSOR = 0, M_ERR = 1, M_NTOTAL = 2, M_DEEP = 3, M_MAXSPAN = 4, M_WORDS = 8 };
 
 namespace {
 
@@ -138,6 +138,8 @@ KParams make_params(clb_ctx *c) {
     P.rec_cursor = (uint32_t *)c->misc.p + M_CURSOR;
     P.win_tab = (uint2 *)c->win_tab.p;
     P.err = (uint32_t *)c->misc.p + M_ERR;
+    P.deep_count = (uint32_t *)c->misc.p + M_DEEP; P.deep_list = (uint32_t *)c->deep_list.p;
+    P.max_low_mapq_fraction = c->opt.max_low_mapq_fraction;
     P.timing = (long long *)c->timing.p;
     if (c->dbg) {
         P.dbg_raw = (uint32_t *)c->dbg_raw.p; P.dbg_qc = (uint32_t *)c->dbg_qc.p;
@@ -167,12 +169,19 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
 int reset_accumulators(clb_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->stats_padded.p, 0, (size_t)N_STATS * STAT_STRIDE * 8, ctx->s_compute));
     CU(cudaMemsetAsync(ctx->counters.p, 0, ((size_t)N_STATS + 3 * (size_t)ctx->n_bins) * 8, ctx->s_compute));
-    CU(cudaMemsetAsync((uint32_t *)ctx->misc.p + M_CURSOR, 0, 3 * sizeof(uint32_t), ctx->s_compute));   // cursor, err, n_total
+    CU(cudaMemsetAsync((uint32_t *)ctx->misc.p + M_CURSOR, 0, 4 * sizeof(uint32_t), ctx->s_compute));   // cursor, err, n_total, deep windows
     return CLB_OK;
 }
 
 int launch_compaction(clb_ctx *ctx) {
     if (ctx->n_windows == 0) return CLB_OK;
+    {
+        // windows with more than 65535 candidate reads were queued by the main pass (normally none)
+        const KParams P = make_params(ctx);
+        if (ctx->opt.min_base_quality >= 128) k_pileup_classify_deep<true><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+        else k_pileup_classify_deep<false><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+        ctx->launches += 1;
+    }
     k_scan_windows<<<1, 1024, 0, ctx->s_compute>>>((const uint2 *)ctx->win_tab.p, ctx->n_windows, (uint32_t *)ctx->win_out.p,
                                                   (uint32_t *)ctx->misc.p + M_NTOTAL);
     const uint32_t warps_per_block = 8;
@@ -194,6 +203,7 @@ int alloc_outputs(clb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->win_rlo, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_rhi, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_out, nw * 4, false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->deep_list, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->rec, (size_t)ctx->rec_cap * 8, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->intervals, (size_t)ctx->rec_cap * sizeof(IntervalOut), false, ctx->s_compute))) return rc;
     return CLB_OK;
@@ -210,7 +220,6 @@ int fetch_result(clb_ctx *ctx, clb_contig_result *out) {
     if (e & ERR_UNSORTED) return fail(ctx, CLB_E_INPUT, "read columns are not coordinate sorted (or pos < 0)");
     if (e & ERR_OFFSETS) return fail(ctx, CLB_E_INPUT, "cigar_off / qual_off are not monotone");
     if (e & ERR_QUAL_SPAN) return fail(ctx, CLB_E_UNSUPPORTED, "a window's candidate reads span more than 4 GiB of qualities");
-    if (e & ERR_DEPTH) return fail(ctx, CLB_E_UNSUPPORTED, "more than 65535 candidate reads in one window (16-bit counters)");
     if (e & ERR_REC_OVERFLOW) return 1;   // caller grows the record buffer and re-runs
     const uint64_t n_iv = ctx->n_windows ? ctx->h_misc[M_NTOTAL] : 0;
     if (n_iv > ctx->h_intervals_cap) {
@@ -307,7 +316,9 @@ clb_ctx *clb_create(int device, const clb_options *opt, char *err, size_t err_le
     ctx->s_compute = ctx->s_own;
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     if ((e = cudaFuncSetAttribute(k_pileup_classify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) {
+        (e = cudaFuncSetAttribute(k_pileup_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pileup_classify_deep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_DEEP)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pileup_classify_deep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_DEEP)) != cudaSuccess) {
         clb_destroy(ctx); return bail("cudaFuncSetAttribute(smem)", e);
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_classify<false>, NT, SMEM_BYTES);
@@ -325,7 +336,7 @@ void clb_destroy(clb_ctx *ctx) {
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end, &ctx->cigar_ckpt,
                       &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_rlo,
-                      &ctx->win_rhi, &ctx->win_out, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
+                      &ctx->win_rhi, &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
         release(*b);
     if (ctx->d_first_tab) cudaFree(ctx->d_first_tab);
     if (ctx->h_intervals) cudaFreeHost(ctx->h_intervals);

@@ -51,7 +51,7 @@ constexpr int STAT_STRIDE = 16;       // one 128-byte line per global counter (u
 
 enum { ST_REF_N = 0, ST_CALLABLE = 1, ST_NO_COVERAGE = 2, ST_LOW_COVERAGE = 3, ST_EXCESSIVE = 4, ST_POOR_MAPQ = 5 };
 enum { S_COUNT0 = 0, S_COVERED = 6, S_SUMCOV = 7, S_SUMBQ = 8, S_SUMMAPQ = 9, S_QBASES = 10, S_RESERVED = 11, N_STATS = 12 };
-enum { ERR_QUAL_SPAN = 1, ERR_REC_OVERFLOW = 2, ERR_DEPTH = 4, ERR_UNSORTED = 8, ERR_OFFSETS = 16 };
+enum { ERR_QUAL_SPAN = 1, ERR_REC_OVERFLOW = 2, ERR_UNSORTED = 8, ERR_OFFSETS = 16 };
 
 struct KParams {
     // packed read columns (device)
@@ -71,6 +71,7 @@ struct KParams {
     uint32_t min_depth, max_depth, min_depth_for_low_mapq;
     uint32_t min_mapq, min_bq, max_low_mapq;
     const uint32_t *first_tab;     // [65536] smallest low count with low/raw > fraction (f64, exact)
+    double max_low_mapq_fraction;  // for depths past the table (deep windows)
     // windows
     const uint32_t *win_rlo, *win_rhi;
     uint32_t win_first;
@@ -83,6 +84,7 @@ struct KParams {
     uint32_t *rec_cursor;
     uint2 *win_tab;                // per window: (first record, record count)
     uint32_t *err;
+    uint32_t *deep_count, *deep_list;   // windows with more than 65535 candidate reads, left to k_pileup_classify_deep
     // optional per-base debug output, indexed by position - region_start
     uint32_t *dbg_raw, *dbg_qc, *dbg_low;
     uint8_t *dbg_state;
@@ -114,6 +116,7 @@ struct Win {
     uint64_t qbase;                // 16-byte aligned byte offset of the window's first candidate quality
     const uint8_t *qual;
     uint32_t sA, sB;               // shared addresses of the difference arrays
+    uint32_t sL;                   // deep windows only: low-MAPQ difference array (otherwise packed into the high half of sA)
     uint32_t min_bq, min_mapq, max_low_mapq;
     bool lq_packed;                // low-BQ counters: KLQ packed-u8 arrays (fast) or one u32 per position
 };
@@ -160,13 +163,20 @@ __device__ __forceinline__ bool emit_m(const Win &W, uint32_t lq_arr, int rel, u
 }
 
 // Difference-array update for a whole read (raw depth + low-MAPQ depth packed as lo16|hi16).  rel/rel_end: entries.
+template <bool WIDE>
 __device__ __forceinline__ void emit_read(const Win &W, int rel, int rel_end, uint32_t mq, unsigned long long &acc_mapq) {
     const int s = max(rel, 0), e = min(rel_end, (int)W.n_ent);
     if (e <= s) return;
     const uint32_t e0 = (uint32_t)s, e1 = (uint32_t)e;
-    const uint32_t delta = 1u + ((mq <= W.max_low_mapq) ? 0x10000u : 0u);
+    const bool lowq = mq <= W.max_low_mapq;
+    const uint32_t delta = 1u + ((lowq && !WIDE) ? 0x10000u : 0u);
+    const uint32_t o1 = 4u * min(e1, (uint32_t)WN - 1u);
     red_shared(W.sA + 4u * e0, delta);
-    red_shared_nz(W.sA + 4u * min(e1, (uint32_t)WN - 1u), e1 < (uint32_t)WN ? 0u - delta : 0u);
+    red_shared_nz(W.sA + o1, e1 < (uint32_t)WN ? 0u - delta : 0u);
+    if (WIDE && lowq) {
+        red_shared(W.sL + 4u * e0, 1u);
+        red_shared_nz(W.sL + o1, e1 < (uint32_t)WN ? 0xffffffffu : 0u);
+    }
     const uint32_t rs = max(e0, 1u);
     if (mq >= W.min_mapq && e1 > rs) acc_mapq += (unsigned long long)mq * (e1 - rs);
 }
@@ -261,7 +271,7 @@ __device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint3
 // Warp-collective expansion of one long CIGAR: 32 ops per step (blocks aligned to 32 ops of the contig-wide CIGAR column),
 // shuffle prefix sums over the (reference, query) lengths, one M-segment per lane streamed right away.  With checkpoints
 // (k_cigar_checkpoints) the walk starts at the last block that begins at or left of the window instead of at the read start.
-template <bool BQ_HI>
+template <bool BQ_HI, bool WIDE>
 __device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P, uint32_t sLQ_s, uint32_t slab, int crel, uint32_t cmq,
                                                  uint32_t c0, uint32_t cn, uint32_t clq, uint64_t cq0, uint2 *myDesc, const uint32_t *sRcp,
                                                  const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum,
@@ -328,11 +338,23 @@ __device__ __forceinline__ void expand_long_read(const Win &W, const KParams &P,
         if (rp_carry >= (int)W.n_ent) break;                          // rest of the read lies right of the window
         ob = bend; v = vn;
     }
-    if (lane == 0) emit_read(W, crel, rp_carry, cmq, acc_mapq);
+    if (lane == 0) emit_read<WIDE>(W, crel, rp_carry, cmq, acc_mapq);
 }
 
 // shared memory: A | B | LQ (KLQ packed-u8 arrays) | masks | first | desc | scan | last | warp stats | next
 constexpr size_t SMEM_COUNTER_WORDS = (size_t)WN * 2 + (size_t)LQ_SLAB * KLQ;
+// Smallest low-MAPQ count in [0, raw + 1] with (double)low / (double)raw > fraction (callable_profiler.rs:100-101):
+// the predicate is monotone in low because IEEE division is monotone.
+__device__ __forceinline__ uint32_t first_low(uint32_t raw, double fraction) {
+    if (raw == 0) return 0xffffffffu;
+    uint32_t lo = 0, hi = raw + 1;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ddiv_rn((double)mid, (double)raw) > fraction) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 #ifndef CLB_DCAP
 #define CLB_DCAP 1024
 #endif
@@ -342,10 +364,13 @@ constexpr int CPLX_CAP = BPR * 32;    // long-CIGAR reads queued per round for C
 constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 + NRCP * 4 + (size_t)(NWARPS * 32 + DCAP) * 8 + 64 * 4 + NT
                             + (size_t)NWARPS * N_STATS * 8 + 128 + 2 * CPLX_CAP * 4;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
+constexpr size_t SMEM_BYTES_DEEP = SMEM_BYTES + (size_t)WN * 4;      // + the separate low-MAPQ difference array
 static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region is zeroed with 16-byte stores");
 
-template <bool BQ_HI>
-__global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams P) {
+// One window.  WIDE = false packs the raw and low-MAPQ depths as 16 + 16 bits (windows with <= 65535 candidate reads, i.e.
+// practically all of them); WIDE = true keeps them in two 32-bit arrays and is only instantiated by k_pileup_classify_deep.
+template <bool BQ_HI, bool WIDE>
+__device__ __forceinline__ void pileup_classify_window(const KParams &P, const uint32_t w) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *sB = sA + WN;
@@ -361,15 +386,15 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     unsigned long long *sWStats = reinterpret_cast<unsigned long long *>(sLast + NT);
     uint32_t *sCtl = reinterpret_cast<uint32_t *>(sWStats + NWARPS * N_STATS);   // [parity][next batch, pool count, pool max chunks]
 
+    uint32_t *sLowD = reinterpret_cast<uint32_t *>(smem_raw + SMEM_BYTES);       // WIDE only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t w = P.win_first + blockIdx.x;
 #define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
     CLB_STAMP(0);
 
     Win W;
     W.wb = (long long)P.region_start + (long long)w * WREAL - 1;
     W.wend = min(W.wb + WN, (long long)P.region_end);
-    W.qual = P.qual; W.sA = smem_addr(sA); W.sB = smem_addr(sB);
+    W.qual = P.qual; W.sA = smem_addr(sA); W.sB = smem_addr(sB); W.sL = WIDE ? smem_addr(sLowD) : 0u;
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
     W.n_ent = n_ent;
@@ -380,10 +405,14 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     W.qbase = 0;
     if (r_hi > r_lo) {
         W.qbase = P.qual_off[r_lo] & ~15ull;
-        if (P.qual_off[r_hi] - W.qbase > 0xfffffff0ull || r_hi - r_lo > 65535u) {
-            // 16-bit depth fields and 32-bit quality offsets cannot represent this window
-            if (tid == 0) atomicOr(P.err, (r_hi - r_lo > 65535u) ? ERR_DEPTH : ERR_QUAL_SPAN);
-            if (tid == 0) P.win_tab[w] = make_uint2(0, 0);
+        if (P.qual_off[r_hi] - W.qbase > 0xfffffff0ull) {
+            // 32-bit quality offsets cannot represent this window
+            if (tid == 0) { atomicOr(P.err, ERR_QUAL_SPAN); P.win_tab[w] = make_uint2(0, 0); }
+            return;
+        }
+        if (!WIDE && r_hi - r_lo > 65535u) {
+            // the 16-bit depth fields could overflow: queue the window for the deep pass
+            if (tid == 0) { P.deep_list[atomicAdd(P.deep_count, 1u)] = w; P.win_tab[w] = make_uint2(0, 0); }
             return;
         }
     }
@@ -393,6 +422,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         uint4 *z = reinterpret_cast<uint4 *>(sA);
         const int nz = (int)((2 * WN + (W.lq_packed ? n_lq : (uint32_t)KLQ) * LQ_SLAB) / 4);
         for (int i = tid; i < nz; i += NT) z[i] = make_uint4(0, 0, 0, 0);
+        if (WIDE) for (int i = tid; i < WN; i += NT) sLowD[i] = 0u;
     }
     if (tid < 17) {
         uint32_t lo[4], hi[4];
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
                 if (((0x18du >> op) & 1u) && rp < (int)WN) rp += (int)len;   // M, D, N, =, X consume the reference (saturates right of the window)
                 if ((0x193u >> op) & 1u) qp += len;                          // M, I, S, =, X consume the query
             }
-            if (nfast) emit_read(W, rel, rp, mq, acc_mapq);
+            if (nfast) emit_read<WIDE>(W, rel, rp, mq, acc_mapq);
         }
         {
             // pool append (warp-aggregated)
@@ -546,7 +576,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
             const uint32_t c0 = P.cigar_off[r], c1 = P.cigar_off[r + 1];
             const uint64_t q0 = P.qual_off[r], ql = P.qual_off[r + 1] - q0;
             const uint32_t bi = (r - r_lo) >> 5;
-            expand_long_read<BQ_HI>(W, P, sLQ_s, W.lq_packed ? bi / BPA : 0u, (int)((long long)P.pos[r] - W.wb), P.mapq[r], c0, c1 - c0,
+            expand_long_read<BQ_HI, WIDE>(W, P, sLQ_s, W.lq_packed ? bi / BPA : 0u, (int)((long long)P.pos[r] - W.wb), P.mapq[r], c0, c1 - c0,
                                     ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql, q0, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum,
                                     acc_mapq, lane);
         }
@@ -558,13 +588,17 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
 
     // ------------------------------------------------------------------ phase C: scan, classify, segment
     const uint32_t ebase = tid * PPT;
-    uint32_t a[PPT], b[PPT], lqv[PPT];
+    uint32_t a[PPT], b[PPT], lqv[PPT], lw[WIDE ? PPT : 1];
     {
 #pragma unroll
         for (int g = 0; g < PPT / 4; g++) {
             const uint4 av = *reinterpret_cast<const uint4 *>(sA + ebase + 4 * g), bv = *reinterpret_cast<const uint4 *>(sB + ebase + 4 * g);
             a[4 * g] = av.x; a[4 * g + 1] = av.y; a[4 * g + 2] = av.z; a[4 * g + 3] = av.w;
             b[4 * g] = bv.x; b[4 * g + 1] = bv.y; b[4 * g + 2] = bv.z; b[4 * g + 3] = bv.w;
+        }
+        if (WIDE) {
+#pragma unroll
+            for (int k = 0; k < PPT; k++) lw[WIDE ? k : 0] = sLowD[ebase + k];
         }
         if (W.lq_packed) {
             uint32_t ev[PPT / 4], od[PPT / 4];                  // 16-bit pair accumulators (4 entries per word)
@@ -588,22 +622,23 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         }
     }
 #pragma unroll
-    for (int k = 1; k < PPT; k++) { a[k] += a[k - 1]; b[k] += b[k - 1]; }
+    for (int k = 1; k < PPT; k++) { a[k] += a[k - 1]; b[k] += b[k - 1]; if (WIDE) lw[WIDE ? k : 0] += lw[WIDE ? k - 1 : 0]; }
     {
-        const uint32_t ta = a[PPT - 1], tb = b[PPT - 1];
-        uint32_t ia = ta, ib = tb;
+        const uint32_t ta = a[PPT - 1], tb = b[PPT - 1], tl = WIDE ? lw[WIDE ? PPT - 1 : 0] : 0u;
+        uint32_t ia = ta, ib = tb, il = tl;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
             const uint32_t t1 = __shfl_up_sync(FULL, ia, dd), t2 = __shfl_up_sync(FULL, ib, dd);
             if (lane >= dd) { ia += t1; ib += t2; }
+            if (WIDE) { const uint32_t t3 = __shfl_up_sync(FULL, il, dd); if (lane >= dd) il += t3; }
         }
-        if (lane == 31) { sScan[warp] = ia; sScan[NWARPS + warp] = ib; }
+        if (lane == 31) { sScan[warp] = ia; sScan[NWARPS + warp] = ib; if (WIDE) sScan[4 * NWARPS + warp] = il; }
         __syncthreads();
-        uint32_t oa = ia - ta, ob = ib - tb;
+        uint32_t oa = ia - ta, ob = ib - tb, ol = il - tl;
 #pragma unroll
-        for (int j = 0; j < NWARPS - 1; j++) { if (j < warp) { oa += sScan[j]; ob += sScan[NWARPS + j]; } }
+        for (int j = 0; j < NWARPS - 1; j++) { if (j < warp) { oa += sScan[j]; ob += sScan[NWARPS + j]; if (WIDE) ol += sScan[4 * NWARPS + j]; } }
 #pragma unroll
-        for (int k = 0; k < PPT; k++) { a[k] += oa; b[k] += ob; }
+        for (int k = 0; k < PPT; k++) { a[k] += oa; b[k] += ob; if (WIDE) lw[WIDE ? k : 0] += ol; }
     }
     // REF_N bits of this thread's entries
     uint32_t nbits;
@@ -618,14 +653,15 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
     using stp_t = typename std::conditional<(PPT > 8), unsigned long long, uint32_t>::type;
     stp_t stp = 0;                                                         // 4 bits of state per entry
     uint32_t cnt_pack = 0, covered = 0, sraw = 0, sqc = 0;
+    unsigned long long sraw_w = 0, sqc_w = 0;                              // deep windows: 32-bit partial sums could overflow
     const uint32_t min_dflm = P.min_depth_for_low_mapq, min_depth = P.min_depth;
     const uint32_t max_depth = P.max_depth ? P.max_depth : 0xffffffffu;   // max_depth == 0 disables EXCESSIVE_COVERAGE
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        const uint32_t raw = a[k] & 0xffffu, low = a[k] >> 16;
+        const uint32_t raw = WIDE ? a[k] : a[k] & 0xffffu, low = WIDE ? lw[WIDE ? k : 0] : a[k] >> 16;
         const uint32_t qc = b[k] - lqv[k];
         uint32_t fst = sFirst[min(raw, (uint32_t)NFIRST - 1u)];
-        if (raw >= (uint32_t)NFIRST) fst = P.first_tab[raw];              // deep positions only
+        if (raw >= (uint32_t)NFIRST) fst = (WIDE && raw >= 65536u) ? first_low(raw, P.max_low_mapq_fraction) : P.first_tab[raw];   // deep positions only
         const bool is_low = raw >= min_dflm && low >= fst;
         uint32_t s = qc > max_depth ? ST_EXCESSIVE : ST_CALLABLE;
         s = qc < min_depth ? ST_LOW_COVERAGE : s;
@@ -636,14 +672,15 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         const uint32_t valid = (vmask >> k) & 1u;
         cnt_pack += valid << (5 * s);
         covered += (raw > 0 ? 1u : 0u) & valid;
-        sraw += valid ? raw : 0u; sqc += valid ? qc : 0u;
+        if (WIDE) { sraw_w += valid ? raw : 0u; sqc_w += valid ? qc : 0u; }
+        else { sraw += valid ? raw : 0u; sqc += valid ? qc : 0u; }
         b[k] = qc;                                                        // keep qc for the optional debug dump
     }
     if (P.dbg_raw) {
 #pragma unroll
         for (int k = 0; k < PPT; k++) if ((vmask >> k) & 1u) {
             const uint32_t o = (uint32_t)(W.wb + (long long)(ebase + k) - P.region_start);
-            P.dbg_raw[o] = a[k] & 0xffffu; P.dbg_qc[o] = b[k]; P.dbg_low[o] = a[k] >> 16; P.dbg_state[o] = (uint8_t)((uint32_t)(stp >> (4 * k)) & 15u);
+            P.dbg_raw[o] = WIDE ? a[k] : a[k] & 0xffffu; P.dbg_qc[o] = b[k]; P.dbg_low[o] = WIDE ? lw[WIDE ? k : 0] : a[k] >> 16; P.dbg_state[o] = (uint8_t)((uint32_t)(stp >> (4 * k)) & 15u);
         }
     }
     sLast[tid] = (uint8_t)((uint32_t)(stp >> (4 * (PPT - 1))) & 15u);
@@ -655,14 +692,18 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
         v[6] = covered; v[7] = sraw; v[8] = acc_sum; v[9] = sqc;
 #pragma unroll
         for (int i = 0; i < 10; i++) v[i] = __reduce_add_sync(FULL, v[i]);
-        unsigned long long mqs = acc_mapq;
+        unsigned long long mqs = acc_mapq, bqs = acc_sum;
 #pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) mqs += __shfl_xor_sync(FULL, mqs, dd);
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            mqs += __shfl_xor_sync(FULL, mqs, dd);
+            if (WIDE) { sraw_w += __shfl_xor_sync(FULL, sraw_w, dd); sqc_w += __shfl_xor_sync(FULL, sqc_w, dd); bqs += __shfl_xor_sync(FULL, bqs, dd); }
+        }
         if (lane == 0) {
             unsigned long long *ws = sWStats + warp * N_STATS;
 #pragma unroll
             for (int s = 0; s < 6; s++) ws[S_COUNT0 + s] = v[s];
-            ws[S_COVERED] = v[6]; ws[S_SUMCOV] = v[7]; ws[S_SUMBQ] = v[8]; ws[S_QBASES] = v[9]; ws[S_RESERVED] = 0; ws[S_SUMMAPQ] = mqs;
+            ws[S_COVERED] = v[6]; ws[S_SUMCOV] = WIDE ? sraw_w : v[7]; ws[S_SUMBQ] = WIDE ? bqs : v[8]; ws[S_QBASES] = WIDE ? sqc_w : v[9];
+            ws[S_RESERVED] = 0; ws[S_SUMMAPQ] = mqs;
         }
     }
     __syncthreads();
@@ -764,6 +805,22 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams 
 #undef CLB_STAMP
 }
 
+template <bool BQ_HI>
+__global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams P) {
+    pileup_classify_window<BQ_HI, false>(P, P.win_first + blockIdx.x);
+}
+
+// Second pass over the (rare) windows k_pileup_classify queued because they hold more than 65535 candidate reads:
+// a fixed small grid walks the queue; with an empty queue the launch costs a few microseconds.
+template <bool BQ_HI>
+__global__ void __launch_bounds__(NT, 1) k_pileup_classify_deep(const KParams P) {
+    const uint32_t n = *P.deep_count;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        pileup_classify_window<BQ_HI, true>(P, P.deep_list[i]);
+        __syncthreads();                                     // shared memory is reused by the next window
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Small helper kernels
 // ---------------------------------------------------------------------------------------------
@@ -853,13 +910,7 @@ __global__ void k_nmask_from_ascii(const uint8_t *ref, uint64_t ref_len, uint32_
 __global__ void k_first_table(uint32_t *first_tab, double fraction) {
     const uint32_t raw = blockIdx.x * blockDim.x + threadIdx.x;
     if (raw >= 65536u) return;
-    if (raw == 0) { first_tab[0] = 0xffffffffu; return; }
-    uint32_t lo = 0, hi = raw + 1;                         // predicate is monotone in low (IEEE division is monotone)
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ddiv_rn((double)mid, (double)raw) > fraction) hi = mid; else lo = mid + 1;
-    }
-    first_tab[raw] = lo;
+    first_tab[raw] = first_low(raw, fraction);
 }
 
 // ---------------------------------------------------------------------------------------------

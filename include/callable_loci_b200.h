@@ -34,7 +34,7 @@ enum {
     CLB_E_CUDA = -2,        /* CUDA runtime error (no device, OOM, launch failure)     */
     CLB_E_INPUT = -3,       /* malformed columns: unsorted pos, offsets not monotone,
                                read past the contig end                                */
-    CLB_E_UNSUPPORTED = -4, /* e.g. a window's reads span more than 4 GiB of qualities */
+    CLB_E_UNSUPPORTED = -4, /* a window's candidate reads span more than 4 GiB of qualities; NCCL not available */
     CLB_E_IO = -5
 };
 

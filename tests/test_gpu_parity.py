@@ -224,3 +224,45 @@ def test_intervals_tile_the_contig_and_alternate(ctx_default):
     assert np.array_equal(np.bincount(iv["state"], weights=lens, minlength=6).astype(np.int64), r.state_counts.astype(np.int64))
     assert r.summed_coverage == int(reads.ref_len().sum())
     assert r.n_covered_bases >= int(r.state_counts[1] + r.state_counts[3] + r.state_counts[4] + r.state_counts[5])
+
+
+def _pile(rng, n, length, same_start, with_indels):
+    """n reads over a short contig: random or identical starts, 1-3 ops, random MAPQ / qualities / flags."""
+    pos = np.zeros(n, np.int64) if same_start else np.sort(rng.integers(0, max(1, length - 70), n))
+    m1 = rng.integers(20, 40, n)
+    three = (rng.random(n) < 0.3) if with_indels else np.zeros(n, bool)
+    gap = rng.integers(1, 5, n); m2 = rng.integers(5, 25, n)
+    is_del = rng.random(n) < 0.5
+    nops = np.where(three, 3, 1)
+    cigar_off = np.concatenate([[0], np.cumsum(nops)])
+    cigar = np.zeros(int(cigar_off[-1]), np.uint32)
+    cigar[cigar_off[:-1]] = (m1 << 4) | 0
+    t = np.nonzero(three)[0]
+    cigar[cigar_off[t] + 1] = (gap[t] << 4) | np.where(is_del[t], 2, 1)
+    cigar[cigar_off[t] + 2] = (m2[t] << 4) | 0
+    qlen = m1 + np.where(three, m2 + np.where(is_del, 0, gap), 0)
+    qual_off = np.concatenate([[0], np.cumsum(qlen)])
+    qual = rng.integers(2, 42, int(qual_off[-1])).astype(np.uint8)
+    mapq = rng.choice(np.array([0, 1, 5, 30, 60], np.uint8), n, p=[.2, .1, .1, .2, .4])
+    flag = rng.choice(np.array([0, 16, 1024, 4], np.uint16), n, p=[.5, .4, .08, .02])
+    return ReadColumns(pos, flag, mapq, cigar_off, cigar, qual_off, qual, np.arange(n, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("same_start", [False, True])
+def test_more_than_65535_reads_in_one_window(same_start):
+    """Windows whose candidate count does not fit the packed 16-bit depth fields take the second (32-bit) pass; with
+    identical starts the raw depth itself passes 65535 and the low-MAPQ threshold is computed past the lookup table."""
+    rng = np.random.default_rng(4242 + int(same_start))
+    length = 2 * WREAL + 300                                   # deep windows next to an ordinary, shallow one
+    reads = _pile(rng, 70_000, WREAL - 100, same_start, with_indels=not same_start)
+    tail = _pile(rng, 300, 250, False, True)
+    tail.pos += 2 * WREAL
+    both = ReadColumns(np.concatenate([reads.pos, tail.pos]), np.concatenate([reads.flag, tail.flag]), np.concatenate([reads.mapq, tail.mapq]),
+                       np.concatenate([reads.cigar_off, tail.cigar_off[1:] + reads.cigar_off[-1]]), np.concatenate([reads.cigar, tail.cigar]),
+                       np.concatenate([reads.qual_off, tail.qual_off[1:] + reads.qual_off[-1]]), np.concatenate([reads.qual, tail.qual]),
+                       np.arange(reads.n + tail.n, dtype=np.uint32))
+    ref = bytes(rng.choice(list(b"ACGTN"), size=length, p=[.245, .245, .245, .245, .02]).tolist())
+    for opt in (CallableOptions(max_depth=100_000, max_low_mapq_fraction=0.3), CallableOptions(max_depth=0, min_depth=1, max_low_mapq=5)):
+        o, _ = assert_parity([("chrD", 0, length, ref, both)], opt)
+        if opt.max_depth:
+            assert o.contigs[0].n_admitted > 65_535 and (not same_start or max(o.contigs[0].counts) > 0)
