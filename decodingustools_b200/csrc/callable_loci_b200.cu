@@ -53,7 +53,7 @@ struct clb_ctx {
 
     DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end, cigar_ckpt;
     DevBuf nmask, ref_ascii;
-    DevBuf stats_padded, counters, rec, win_tab, win_rlo, win_rhi, win_out, deep_list, intervals, misc;
+    DevBuf stats_padded, counters, rec, win_tab, win_r, win_q, win_out, deep_list, intervals, misc;
     DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state, timing;
     uint32_t rec_cap = 0;
     bool dbg = false;
@@ -130,7 +130,7 @@ KParams make_params(clb_ctx *c) {
     P.min_depth = c->opt.min_depth; P.max_depth = c->opt.max_depth; P.min_depth_for_low_mapq = c->opt.min_depth_for_low_mapq;
     P.min_mapq = c->opt.min_mapping_quality; P.min_bq = c->opt.min_base_quality; P.max_low_mapq = c->opt.max_low_mapq;
     P.first_tab = c->d_first_tab;
-    P.win_rlo = (const uint32_t *)c->win_rlo.p; P.win_rhi = (const uint32_t *)c->win_rhi.p;
+    P.win_r = (const uint2 *)c->win_r.p; P.win_q = (const ulonglong2 *)c->win_q.p;
     P.stats = (unsigned long long *)c->stats_padded.p;
     P.bins = (unsigned long long *)c->counters.p + N_STATS;
     P.n_bins = c->n_bins; P.stride = c->stride;
@@ -154,7 +154,8 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     const uint32_t n = w1 - w0;
     k_window_ranges<<<(n + 127) / 128, 128, 0, ctx->s_compute>>>(
         (const int32_t *)ctx->pos.p, (uint32_t)ctx->n_reads, ctx->region_start, ctx->region_end,
-        (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (uint32_t *)ctx->win_rlo.p, (uint32_t *)ctx->win_rhi.p);
+        (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p,
+        (uint2 *)ctx->win_r.p, (ulonglong2 *)ctx->win_q.p);
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
@@ -200,8 +201,8 @@ int alloc_outputs(clb_ctx *ctx) {
     int rc;
     const size_t nw = std::max<size_t>(ctx->n_windows, 1);
     if ((rc = ensure(ctx, ctx->win_tab, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
-    if ((rc = ensure(ctx, ctx->win_rlo, nw * 4, false, ctx->s_compute))) return rc;
-    if ((rc = ensure(ctx, ctx->win_rhi, nw * 4, false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->win_r, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->win_q, nw * sizeof(ulonglong2), false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_out, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->deep_list, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->rec, (size_t)ctx->rec_cap * 8, false, ctx->s_compute))) return rc;
@@ -335,8 +336,8 @@ void clb_destroy(clb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end, &ctx->cigar_ckpt,
-                      &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_rlo,
-                      &ctx->win_rhi, &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
+                      &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_r,
+                      &ctx->win_q, &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
         release(*b);
     if (ctx->d_first_tab) cudaFree(ctx->d_first_tab);
     if (ctx->h_intervals) cudaFreeHost(ctx->h_intervals);

@@ -73,7 +73,8 @@ struct KParams {
     const uint32_t *first_tab;     // [65536] smallest low count with low/raw > fraction (f64, exact)
     double max_low_mapq_fraction;  // for depths past the table (deep windows)
     // windows
-    const uint32_t *win_rlo, *win_rhi;
+    const uint2 *win_r;            // per window: candidate reads [x, y)
+    const ulonglong2 *win_q;       // per window: quality bytes [x (16-byte aligned), y) of the candidate reads
     uint32_t win_first;
     // outputs
     unsigned long long *stats;     // [N_STATS * STAT_STRIDE]
@@ -90,6 +91,14 @@ struct KParams {
     uint8_t *dbg_state;
     long long *timing;             // optional (developer builds): 8 clock64 stamps per window
 };
+
+// One bulk L2 prefetch of bytes [lo, hi) of a device array (rounded out to 16 bytes: allocations are 256-byte granular).
+__device__ __forceinline__ void l2_prefetch(const void *base, uint64_t lo, uint64_t hi, uint32_t max_bytes) {
+    const uint64_t a = ((uint64_t)(uintptr_t)base + lo) & ~15ull, b = ((uint64_t)(uintptr_t)base + hi + 15ull) & ~15ull;
+    if (b <= a) return;
+    const uint32_t bytes = (uint32_t)min(b - a, (uint64_t)max_bytes);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     uint4 r;
@@ -355,6 +364,9 @@ __device__ __forceinline__ uint32_t first_low(uint32_t raw, double fraction) {
     return lo;
 }
 
+#ifndef CLB_PREFETCH_MAX
+#define CLB_PREFETCH_MAX (128u << 10)     // bytes of a window's qualities prefetched into L2 at window start
+#endif
 #ifndef CLB_DCAP
 #define CLB_DCAP 1024
 #endif
@@ -398,14 +410,16 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
     W.n_ent = n_ent;
-    const uint32_t r_lo = P.win_rlo[w], r_hi = P.win_rhi[w];
+    const uint2 wr = P.win_r[w];
+    const ulonglong2 wq = P.win_q[w];
+    const uint32_t r_lo = wr.x, r_hi = wr.y;
     const uint32_t n_batches = (r_hi - r_lo + 31u) >> 5;
     const uint32_t n_lq = (n_batches + BPA - 1) / BPA;     // packed arrays needed
     W.lq_packed = n_lq <= (uint32_t)KLQ;
     W.qbase = 0;
     if (r_hi > r_lo) {
-        W.qbase = P.qual_off[r_lo] & ~15ull;
-        if (P.qual_off[r_hi] - W.qbase > 0xfffffff0ull) {
+        W.qbase = wq.x;
+        if (wq.y - W.qbase > 0xfffffff0ull) {
             // 32-bit quality offsets cannot represent this window
             if (tid == 0) { atomicOr(P.err, ERR_QUAL_SPAN); P.win_tab[w] = make_uint2(0, 0); }
             return;
@@ -416,6 +430,10 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
             return;
         }
     }
+    // The window's qualities are one contiguous byte range that phase B streams after the CIGAR walk: start pulling it
+    // into L2 now (one bulk prefetch: no registers, no shared memory).  Prefetching the inputs of the window one wave
+    // of CTAs further on as well was measured and lost 3-6 %.
+    if (tid == 0) l2_prefetch(P.qual, wq.x, wq.y, CLB_PREFETCH_MAX);
 
     {
         // zero the difference arrays and only the low-BQ slabs this window will use
@@ -832,15 +850,17 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t
 
 // candidate read range of every window: reads with pos < window end and pos + max_span > halo position
 __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t region_start, uint32_t region_end,
-                                const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w, uint32_t *win_rlo, uint32_t *win_rhi) {
+                                const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w,
+                                const uint64_t *qual_off, uint2 *win_r, ulonglong2 *win_q) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_w) return;
     const uint32_t max_span = *max_span_ptr;
     const uint32_t w = w_first + i;
     const long long wb = (long long)region_start + (long long)w * WREAL - 1;
     const long long wend = min(wb + WN, (long long)region_end);
-    win_rlo[w] = lower_bound_pos(pos, n_reads, wb - (long long)max_span + 1);
-    win_rhi[w] = lower_bound_pos(pos, n_reads, wend);
+    const uint32_t r_lo = lower_bound_pos(pos, n_reads, wb - (long long)max_span + 1), r_hi = lower_bound_pos(pos, n_reads, wend);
+    win_r[w] = make_uint2(r_lo, r_hi);
+    win_q[w] = make_ulonglong2(qual_off[r_lo] & ~15ull, qual_off[r_hi]);
 }
 
 // pos + reference span of every read, and the maximum span (long-read mode / max_ref_span == 0)
