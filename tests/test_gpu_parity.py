@@ -245,7 +245,41 @@ def _pile(rng, n, length, same_start, with_indels):
     qual = rng.integers(2, 42, int(qual_off[-1])).astype(np.uint8)
     mapq = rng.choice(np.array([0, 1, 5, 30, 60], np.uint8), n, p=[.2, .1, .1, .2, .4])
     flag = rng.choice(np.array([0, 16, 1024, 4], np.uint16), n, p=[.5, .4, .08, .02])
-    return ReadColumns(pos, flag, mapq, cigar_off, cigar, qual_off, qual, np.arange(n, dtype=np.uint32))
+    rc = ReadColumns(pos, flag, mapq, cigar_off, cigar, qual_off, qual, np.arange(n, dtype=np.uint32))
+    if not with_indels:
+        return rc
+    # every 50th read gets a 9-op CIGAR (the warp-cooperative long-CIGAR path)
+    recs = []
+    for i in range(n):
+        if i % 50 == 0:
+            ops = [(int(rng.integers(3, 9)), 0)]
+            for _ in range(4):
+                ops += [(int(rng.integers(1, 4)), int(rng.choice([1, 2, 3, 4]))), (int(rng.integers(3, 9)), 0)]
+            ql = sum(l for l, o in ops if o in (0, 1, 4))
+            recs.append((int(pos[i]), int(flag[i]), int(mapq[i]), "".join(f"{l}{'MIDNS'[o]}" for l, o in ops), rng.integers(2, 42, ql).astype(np.uint8).tobytes(), f"l{i}"))
+    longs = ReadColumns.from_records(recs)
+    keep = np.ones(n, bool); keep[::50] = False
+    short = rc.select(keep)
+    order = np.argsort(np.concatenate([short.pos, longs.pos]), kind="stable")
+    both = _concat(short, longs)
+    return _reorder(both, order)
+
+
+def _concat(a, b):
+    return ReadColumns(np.concatenate([a.pos, b.pos]), np.concatenate([a.flag, b.flag]), np.concatenate([a.mapq, b.mapq]),
+                       np.concatenate([a.cigar_off, b.cigar_off[1:] + a.cigar_off[-1]]), np.concatenate([a.cigar, b.cigar]),
+                       np.concatenate([a.qual_off, b.qual_off[1:] + a.qual_off[-1]]), np.concatenate([a.qual, b.qual]),
+                       np.arange(a.n + b.n, dtype=np.uint32))
+
+
+def _reorder(rc, order):
+    """Records of rc in the given order (used to merge two coordinate-sorted sets)."""
+    co, qo = rc.cigar_off.astype(np.int64), rc.qual_off.astype(np.int64)
+    cl, ql = np.diff(co)[order], np.diff(qo)[order]
+    cigar = np.concatenate([rc.cigar[co[i]:co[i + 1]] for i in order]) if len(order) else rc.cigar
+    qual = np.concatenate([rc.qual[qo[i]:qo[i + 1]] for i in order]) if len(order) else rc.qual
+    return ReadColumns(rc.pos[order], rc.flag[order], rc.mapq[order], np.concatenate([[0], np.cumsum(cl)]), cigar,
+                       np.concatenate([[0], np.cumsum(ql)]), qual, np.arange(len(order), dtype=np.uint32))
 
 
 @pytest.mark.parametrize("same_start", [False, True])
@@ -257,10 +291,7 @@ def test_more_than_65535_reads_in_one_window(same_start):
     reads = _pile(rng, 70_000, WREAL - 100, same_start, with_indels=not same_start)
     tail = _pile(rng, 300, 250, False, True)
     tail.pos += 2 * WREAL
-    both = ReadColumns(np.concatenate([reads.pos, tail.pos]), np.concatenate([reads.flag, tail.flag]), np.concatenate([reads.mapq, tail.mapq]),
-                       np.concatenate([reads.cigar_off, tail.cigar_off[1:] + reads.cigar_off[-1]]), np.concatenate([reads.cigar, tail.cigar]),
-                       np.concatenate([reads.qual_off, tail.qual_off[1:] + reads.qual_off[-1]]), np.concatenate([reads.qual, tail.qual]),
-                       np.arange(reads.n + tail.n, dtype=np.uint32))
+    both = _concat(reads, tail)
     ref = bytes(rng.choice(list(b"ACGTN"), size=length, p=[.245, .245, .245, .245, .02]).tolist())
     for opt in (CallableOptions(max_depth=100_000, max_low_mapq_fraction=0.3), CallableOptions(max_depth=0, min_depth=1, max_low_mapq=5)):
         o, _ = assert_parity([("chrD", 0, length, ref, both)], opt)
