@@ -513,13 +513,14 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
                 M[u].nops = live ? c1[u] - c0[u] : 0u; M[u].op0 = op0[u];
             }
         }
-#pragma unroll
+#pragma unroll 1                                                        // one copy of the walk: the executed code has to fit the instruction cache
         for (int u = 0; u < 2; u++) {
         if (i0 + u * NT >= rr1) break;                                   // warp-uniform
         const uint32_t bi = (i0 + u * NT - r_lo) >> 5;
         const uint32_t slab = W.lq_packed ? bi / BPA : 0u;
         const uint32_t lq_arr = sLQ_s + slab * (uint32_t)(LQ_SLAB * 4);
-        const int rel = M[u].rel; const uint32_t mq = M[u].mq, c0 = M[u].c0, nops = M[u].nops, lq = M[u].lq; const uint64_t q0 = M[u].q0;
+        const RMeta Mu = u ? M[1] : M[0];
+        const int rel = Mu.rel; const uint32_t mq = Mu.mq, c0 = Mu.c0, nops = Mu.nops, lq = Mu.lq; const uint64_t q0 = Mu.q0;
         // short CIGARs are walked lane-serially (one loop trip per op, trip count = longest short CIGAR in the warp)
         bool cplx = nops > (uint32_t)FAST_OPS;
         if (__any_sync(FULL, !cplx && nops > 2u)) {                      // <= 2 ops cannot hold more than MAXSEG = 2 segments
@@ -539,7 +540,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
             int rp = rel; uint32_t qp = 0;
             const bool pass = mq >= W.min_mapq;
             for (uint32_t k = 0; k < kmax; k++) {
-                const uint32_t v = k < nfast ? (k == 0 ? M[u].op0 : P.cigar[c0 + k]) : 0xfu;  // op 15, len 0: no effect
+                const uint32_t v = k < nfast ? (k == 0 ? Mu.op0 : P.cigar[c0 + k]) : 0xfu;  // op 15, len 0: no effect
                 const uint32_t op = v & 15u, len = v >> 4;
                 if (((0x181u >> op) & 1u) && pass) {
                     Seg s;
