@@ -71,6 +71,7 @@ struct KParams {
     uint32_t min_depth, max_depth, min_depth_for_low_mapq;
     uint32_t min_mapq, min_bq, max_low_mapq;
     const uint32_t *first_tab;     // [65536] smallest low count with low/raw > fraction (f64, exact)
+    const uint32_t *win_tables;    // WIN_TABLE_BYTES: the per-window shared-memory tables, ready to copy (k_window_tables)
     double max_low_mapq_fraction;  // for depths past the table (deep windows)
     // windows
     const uint2 *win_r;            // per window: candidate reads [x, y)
@@ -377,6 +378,8 @@ constexpr size_t SMEM_BYTES = SMEM_COUNTER_WORDS * 4 + 2 * 17 * 16 + NFIRST * 4 
                             + (size_t)NWARPS * N_STATS * 8 + 128 + 2 * CPLX_CAP * 4;
 static_assert((size_t)KLQ * LQ_SLAB >= (size_t)WN + 32, "the u32-per-position fallback must fit in the packed low-BQ region");
 constexpr size_t SMEM_BYTES_DEEP = SMEM_BYTES + (size_t)WN * 4;      // + the separate low-MAPQ difference array
+constexpr size_t WIN_TABLE_BYTES = 2 * 17 * 16 + NFIRST * 4 + NRCP * 4;   // sMaskLo | sMaskHi | sFirst | sRcp, contiguous in shared memory
+static_assert(WIN_TABLE_BYTES % 16 == 0, "window tables are copied with 16-byte loads");
 static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region is zeroed with 16-byte stores");
 
 // One window.  WIDE = false packs the raw and low-MAPQ depths as 16 + 16 bits (windows with <= 65535 candidate reads, i.e.
@@ -442,23 +445,12 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         for (int i = tid; i < nz; i += NT) z[i] = make_uint4(0, 0, 0, 0);
         if (WIDE) for (int i = tid; i < WN; i += NT) sLowD[i] = 0u;
     }
-    if (tid < 17) {
-        uint32_t lo[4], hi[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t ml = 0, mh = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (4 * q + j < tid) ml |= 0xffu << (8 * j);        // bytes below lo = tid
-                if (4 * q + j >= tid) mh |= 0xffu << (8 * j);       // bytes at/above hi = tid
-            }
-            lo[q] = ml; hi[q] = mh;
-        }
-        sMaskLo[tid] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        sMaskHi[tid] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    {
+        // byte masks, first_tab[0..NFIRST) and the reciprocal table: built once per context (k_window_tables), copied here
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.win_tables);
+        uint4 *dst = sMaskLo;
+        for (int i = tid; i < (int)(WIN_TABLE_BYTES / 16); i += NT) dst[i] = src[i];
     }
-    for (int i = tid; i < NFIRST; i += NT) sFirst[i] = P.first_tab[i];
-    for (int i = tid; i < NRCP; i += NT) sRcp[i] = i > 1 ? 0xffffffffu / (uint32_t)i + 1u : 0u;
     if (tid < 6) sCtl[tid] = 0;
     if (tid >= 16 && tid < 20) sCtl[tid] = 0;                // [16 + 2 * parity]: queued long reads, next to expand
     uint32_t *sCplx = sCtl + 32;                            // [parity][CPLX_CAP] read indices
@@ -928,6 +920,26 @@ __global__ void k_nmask_from_ascii(const uint8_t *ref, uint64_t ref_len, uint32_
 }
 
 // first_tab[raw] = smallest low in [0, raw+1] with (double)low / (double)raw > fraction  (callable_profiler.rs:100-101)
+// The small tables every window keeps in shared memory, laid out as the kernel expects them:
+//   17 x uint4 "bytes below lo" masks | 17 x uint4 "bytes at/above hi" masks | first_tab[0..NFIRST) | ceil(2^32 / i) for i < NRCP
+__global__ void k_window_tables(uint32_t *out, double fraction) {
+    const uint32_t t = threadIdx.x;
+    if (t < 17) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t ml = 0, mh = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (4 * q + j < (int)t) ml |= 0xffu << (8 * j);          // bytes below lo = t
+                if (4 * q + j >= (int)t) mh |= 0xffu << (8 * j);         // bytes at/above hi = t
+            }
+            out[4 * t + q] = ml; out[17 * 4 + 4 * t + q] = mh;
+        }
+    }
+    for (uint32_t i = t; i < (uint32_t)NFIRST; i += blockDim.x) out[2 * 17 * 4 + i] = first_low(i, fraction);
+    for (uint32_t i = t; i < (uint32_t)NRCP; i += blockDim.x) out[2 * 17 * 4 + NFIRST + i] = i > 1 ? 0xffffffffu / i + 1u : 0u;
+}
+
 __global__ void k_first_table(uint32_t *first_tab, double fraction) {
     const uint32_t raw = blockIdx.x * blockDim.x + threadIdx.x;
     if (raw >= 65536u) return;
