@@ -596,8 +596,13 @@ int clb_allreduce_nccl(clb_ctx *ctx, void *nccl_comm) {
     return CLB_OK;
 }
 
-/* developer hook (not part of the public header): per-window clock64 stamps of the next runs */
+/* developer hook (not part of the public header): per-window clock64 stamps of the next runs; needs a library
+ * built with -DCLB_PHASE_TIMING (the stamps are compiled out of production builds) */
 int clb_debug_timing(clb_ctx *ctx, long long *out, uint32_t max_windows, uint32_t *n_windows) {
+#ifndef CLB_PHASE_TIMING
+    (void)out; (void)max_windows; (void)n_windows;
+    return fail(ctx, CLB_E_UNSUPPORTED, "library built without -DCLB_PHASE_TIMING");
+#else
     if (!ctx || !ctx->in_contig || !ctx->finished) return CLB_E_INVALID;
     int rc;
     const size_t n = std::min<size_t>(ctx->n_windows, max_windows);
@@ -608,6 +613,7 @@ int clb_debug_timing(clb_ctx *ctx, long long *out, uint32_t max_windows, uint32_
     if (n_windows) *n_windows = (uint32_t)n;
     release(ctx->timing);
     return CLB_OK;
+#endif
 }
 
 int clb_debug_per_base(clb_ctx *ctx, uint32_t *raw, uint32_t *qc, uint32_t *low, uint8_t *state) {

@@ -403,7 +403,11 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
 
     uint32_t *sLowD = reinterpret_cast<uint32_t *>(smem_raw + SMEM_BYTES);       // WIDE only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef CLB_PHASE_TIMING      // developer builds only (scripts/phase_timing.py): the stamps cost instruction-cache space
 #define CLB_STAMP(i) do { if (P.timing && tid == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
+#else
+#define CLB_STAMP(i) do { } while (0)
+#endif
     CLB_STAMP(0);
 
     Win W;
@@ -812,7 +816,9 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         }
     }
     CLB_STAMP(6);
+#ifdef CLB_PHASE_TIMING
     if (P.timing && tid == 0) { P.timing[(size_t)w * 8 + 7] = (long long)(r_hi - r_lo); }
+#endif
 #undef CLB_STAMP
 }
 

@@ -1,4 +1,7 @@
-"""Developer helper: where does a window's wall time go? (clock64 stamps per CTA via clb_debug_timing)"""
+"""Developer helper: where does a window's wall time go? (clock64 stamps per CTA via clb_debug_timing)
+
+Needs a library built with the stamps: (cd decodingustools_b200/csrc && nvcc <Makefile flags> -DCLB_PHASE_TIMING -shared
+-o ../../variants/lib_timing.so callable_loci_b200.cu clb_host.cpp -ldl), then CLB_LIB=variants/lib_timing.so python scripts/phase_timing.py."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
