@@ -160,8 +160,14 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
-    if (ctx->opt.min_base_quality >= 128) k_pileup_classify<true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
-    else k_pileup_classify<false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+    const bool hi = ctx->opt.min_base_quality >= 128;
+    if (ctx->dbg) {                                      // per-base dump requested (parity tests): separate instantiation
+        if (hi) k_pileup_classify<true, true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+        else k_pileup_classify<false, true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+    } else {
+        if (hi) k_pileup_classify<true, false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+        else k_pileup_classify<false, false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+    }
     if (time_pileup) CU(cudaEventRecord(time_pileup->b, ctx->s_compute));
     ctx->launches += 2;
     CU(cudaGetLastError());
@@ -317,13 +323,15 @@ clb_ctx *clb_create(int device, const clb_options *opt, char *err, size_t err_le
     if ((e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return bail("cudaStreamCreate", e); }
     ctx->s_compute = ctx->s_own;
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
-    if ((e = cudaFuncSetAttribute(k_pileup_classify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(k_pileup_classify<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pileup_classify<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pileup_classify<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pileup_classify<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pileup_classify_deep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_DEEP)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pileup_classify_deep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_DEEP)) != cudaSuccess) {
         clb_destroy(ctx); return bail("cudaFuncSetAttribute(smem)", e);
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_classify<false>, NT, SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_classify<false, false>, NT, SMEM_BYTES);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc((void **)&ctx->d_first_tab, 65536 * 4 + WIN_TABLE_BYTES)) != cudaSuccess) { clb_destroy(ctx); return bail("cudaMalloc", e); }
     k_first_table<<<65536 / 256, 256, 0, ctx->s_compute>>>(ctx->d_first_tab, opt->max_low_mapq_fraction);

@@ -384,7 +384,7 @@ static_assert(SMEM_COUNTER_WORDS % 4 == 0 && LQ_SLAB % 4 == 0, "counter region i
 
 // One window.  WIDE = false packs the raw and low-MAPQ depths as 16 + 16 bits (windows with <= 65535 candidate reads, i.e.
 // practically all of them); WIDE = true keeps them in two 32-bit arrays and is only instantiated by k_pileup_classify_deep.
-template <bool BQ_HI, bool WIDE>
+template <bool BQ_HI, bool WIDE, bool DBG>
 __device__ __forceinline__ void pileup_classify_window(const KParams &P, const uint32_t w) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw);
@@ -691,7 +691,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         else { sraw += valid ? raw : 0u; sqc += valid ? qc : 0u; }
         b[k] = qc;                                                        // keep qc for the optional debug dump
     }
-    if (P.dbg_raw) {
+    if (DBG && P.dbg_raw) {                                                // per-base dump for the parity tests (own instantiation)
 #pragma unroll
         for (int k = 0; k < PPT; k++) if ((vmask >> k) & 1u) {
             const uint32_t o = (uint32_t)(W.wb + (long long)(ebase + k) - P.region_start);
@@ -801,7 +801,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
                     if (c_poor) atomicAdd(&P.bins[P.n_bins + tb0], (unsigned long long)c_poor);
                     if (c_refn) atomicAdd(&P.bins[2 * P.n_bins + tb0], (unsigned long long)c_refn);
                 } else {
-#pragma unroll
+#pragma unroll 1                                                // rare (a thread's entries straddle two bins): keep it small
                     for (int k = 0; k < PPT; k++) {
                         if ((uint32_t)k >= k_first && (uint32_t)k < k_end) {
                             const uint32_t bi = (uint32_t)(W.wb + ebase + k) / P.stride;
@@ -822,9 +822,9 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
 #undef CLB_STAMP
 }
 
-template <bool BQ_HI>
+template <bool BQ_HI, bool DBG>
 __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams P) {
-    pileup_classify_window<BQ_HI, false>(P, P.win_first + blockIdx.x);
+    pileup_classify_window<BQ_HI, false, DBG>(P, P.win_first + blockIdx.x);
 }
 
 // Second pass over the (rare) windows k_pileup_classify queued because they hold more than 65535 candidate reads:
@@ -833,7 +833,7 @@ template <bool BQ_HI>
 __global__ void __launch_bounds__(NT, 1) k_pileup_classify_deep(const KParams P) {
     const uint32_t n = *P.deep_count;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        pileup_classify_window<BQ_HI, true>(P, P.deep_list[i]);
+        pileup_classify_window<BQ_HI, true, true>(P, P.deep_list[i]);
         __syncthreads();                                     // shared memory is reused by the next window
     }
 }
