@@ -131,7 +131,7 @@ KParams make_params(clb_ctx *c) {
     P.min_mapq = c->opt.min_mapping_quality; P.min_bq = c->opt.min_base_quality; P.max_low_mapq = c->opt.max_low_mapq;
     P.first_tab = c->d_first_tab;
     P.win_tables = c->d_first_tab + 65536;
-    P.win_r = (const uint2 *)c->win_r.p; P.win_q = (const ulonglong2 *)c->win_q.p;
+    P.win_r = (const uint4 *)c->win_r.p; P.win_q = (const ulonglong2 *)c->win_q.p;
     P.stats = (unsigned long long *)c->stats_padded.p;
     P.bins = (unsigned long long *)c->counters.p + N_STATS;
     P.n_bins = c->n_bins; P.stride = c->stride;
@@ -155,8 +155,8 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     const uint32_t n = w1 - w0;
     k_window_ranges<<<(n + 127) / 128, 128, 0, ctx->s_compute>>>(
         (const int32_t *)ctx->pos.p, (uint32_t)ctx->n_reads, ctx->region_start, ctx->region_end,
-        (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p,
-        (uint2 *)ctx->win_r.p, (ulonglong2 *)ctx->win_q.p);
+        (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p, ctx->stride,
+        (uint4 *)ctx->win_r.p, (ulonglong2 *)ctx->win_q.p);
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
@@ -208,7 +208,7 @@ int alloc_outputs(clb_ctx *ctx) {
     int rc;
     const size_t nw = std::max<size_t>(ctx->n_windows, 1);
     if ((rc = ensure(ctx, ctx->win_tab, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
-    if ((rc = ensure(ctx, ctx->win_r, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->win_r, nw * sizeof(uint4), false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_q, nw * sizeof(ulonglong2), false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_out, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->deep_list, nw * 4, false, ctx->s_compute))) return rc;

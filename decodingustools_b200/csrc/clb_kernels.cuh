@@ -26,6 +26,7 @@ namespace clb {
 #endif
 constexpr int NT = CLB_NT;            // threads per CTA
 constexpr int NWARPS = NT / 32;
+static_assert(NWARPS <= 32, "cross-warp prefixes are taken with one warp-wide reduction");
 #ifndef CLB_PPT
 #define CLB_PPT 8
 #endif
@@ -74,7 +75,7 @@ struct KParams {
     const uint32_t *win_tables;    // WIN_TABLE_BYTES: the per-window shared-memory tables, ready to copy (k_window_tables)
     double max_low_mapq_fraction;  // for depths past the table (deep windows)
     // windows
-    const uint2 *win_r;            // per window: candidate reads [x, y)
+    const uint4 *win_r;            // per window: candidate reads [x, y), first histogram bin z, window entry w where the next bin starts
     const ulonglong2 *win_q;       // per window: quality bytes [x (16-byte aligned), y) of the candidate reads
     uint32_t win_first;
     // outputs
@@ -417,7 +418,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
     W.n_ent = n_ent;
-    const uint2 wr = P.win_r[w];
+    const uint4 wr = P.win_r[w];
     const ulonglong2 wq = P.win_q[w];
     const uint32_t r_lo = wr.x, r_hi = wr.y;
     const uint32_t n_batches = (r_hi - r_lo + 31u) >> 5;
@@ -461,9 +462,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     if (tid == 0) {                                          // runtime divisions once per CTA instead of once per thread
         const uint32_t nr = (n_batches + BPR - 1) / BPR;
         sCtl[8] = nr; sCtl[9] = nr ? (n_batches + nr - 1) / nr : 0u;
-        const uint32_t first_bin = P.stride ? (uint32_t)(W.wb + 1) / P.stride : 0u;
-        sCtl[10] = first_bin;
-        sCtl[11] = P.stride ? (uint32_t)((long long)(first_bin + 1) * P.stride - W.wb) : 0xffffffffu;   // first entry of the next bin
+        sCtl[10] = wr.z; sCtl[11] = wr.w;                    // first bin, first entry of the next bin (k_window_ranges)
     }
     __syncthreads();
 
@@ -649,9 +648,12 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         }
         if (lane == 31) { sScan[warp] = ia; sScan[NWARPS + warp] = ib; if (WIDE) sScan[4 * NWARPS + warp] = il; }
         __syncthreads();
-        uint32_t oa = ia - ta, ob = ib - tb, ol = il - tl;
-#pragma unroll
-        for (int j = 0; j < NWARPS - 1; j++) { if (j < warp) { oa += sScan[j]; ob += sScan[NWARPS + j]; if (WIDE) ol += sScan[4 * NWARPS + j]; } }
+        // totals of the warps before this one: lane j holds warp j's total, one REDUX per array sums lanes < warp
+        const bool before = lane < warp;
+        uint32_t oa = ia - ta + __reduce_add_sync(FULL, before ? sScan[lane] : 0u);
+        uint32_t ob = ib - tb + __reduce_add_sync(FULL, before ? sScan[NWARPS + lane] : 0u);
+        uint32_t ol = il - tl;
+        if (WIDE) ol += __reduce_add_sync(FULL, before ? sScan[4 * NWARPS + lane] : 0u);
 #pragma unroll
         for (int k = 0; k < PPT; k++) { a[k] += oa; b[k] += ob; if (WIDE) lw[WIDE ? k : 0] += ol; }
     }
@@ -753,9 +755,8 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inb, dd); if (lane >= dd) inb += t; }
         if (lane == 31) sScan[2 * NWARPS + warp] = inb;
         __syncthreads();
-        uint32_t off = inb - nb, total = 0;
-#pragma unroll
-        for (int j = 0; j < NWARPS; j++) { const uint32_t t = sScan[2 * NWARPS + j]; if (j < warp) off += t; total += t; }
+        const uint32_t wt = lane < NWARPS ? sScan[2 * NWARPS + lane] : 0u;             // lane j: boundaries in warp j
+        const uint32_t off = inb - nb + __reduce_add_sync(FULL, lane < warp ? wt : 0u), total = __reduce_add_sync(FULL, wt);
         if (tid == 0) {
             const uint32_t base = total ? atomicAdd(P.rec_cursor, total) : 0u;
             sScan[3 * NWARPS] = base;
@@ -850,7 +851,7 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t
 // candidate read range of every window: reads with pos < window end and pos + max_span > halo position
 __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t region_start, uint32_t region_end,
                                 const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w,
-                                const uint64_t *qual_off, uint2 *win_r, ulonglong2 *win_q) {
+                                const uint64_t *qual_off, uint32_t stride, uint4 *win_r, ulonglong2 *win_q) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_w) return;
     const uint32_t max_span = *max_span_ptr;
@@ -858,7 +859,8 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     const long long wb = (long long)region_start + (long long)w * WREAL - 1;
     const long long wend = min(wb + WN, (long long)region_end);
     const uint32_t r_lo = lower_bound_pos(pos, n_reads, wb - (long long)max_span + 1), r_hi = lower_bound_pos(pos, n_reads, wend);
-    win_r[w] = make_uint2(r_lo, r_hi);
+    const uint32_t first_bin = stride ? (uint32_t)(wb + 1) / stride : 0u;
+    win_r[w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
     win_q[w] = make_ulonglong2(qual_off[r_lo] & ~15ull, qual_off[r_hi]);
 }
 
