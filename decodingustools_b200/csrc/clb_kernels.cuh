@@ -195,7 +195,8 @@ __device__ __forceinline__ void emit_read(const Win &W, int rel, int rel_end, ui
 // One 16-byte quality chunk.  e0 = window entry of chunk byte 0 (may be < 0 or past the window for bytes outside
 // [lo, hi), which are forced to 0xFF so they never fail and are subtracted from the sums).  Straight-line code:
 // shared-memory atomics are cheaper on sm_100a (about one warp-wide ATOMS per clock per SM) than branches around them.
-template <bool BQ_HI>
+// LAYOUT: 1 = packed u8 low-BQ counters, 0 = one u32 per position, 2 = decided per window at run time (W.lq_packed)
+template <bool BQ_HI, int LAYOUT>
 __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int e0, uint32_t lo, uint32_t hi, uint4 v, const uint4 *sMaskLo,
                                               const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc_sum) {
     const uint4 ml = sMaskLo[lo], mh = sMaskHi[hi];       // 0xFF in bytes outside [lo, hi)
@@ -209,7 +210,7 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
     const uint32_t ninv = lo + (16u - hi);
     acc_sum += tot - 255u * ninv - (sf128 >> 7);
     const uint32_t f0 = l0 >> 7, f1 = l1 >> 7, f2 = l2 >> 7, f3 = l3 >> 7;                    // 1 in every failing byte
-    if (W.lq_packed) {
+    if (LAYOUT == 2 ? W.lq_packed : LAYOUT == 1) {
         // four positions per 32-bit word, one byte each: shift the 16 fail flags to the entry alignment and add them
         // with five unconditional atomics (a byte takes <= 224 increments, see BPA).
         const uint32_t sh = ((uint32_t)e0 & 3u) << 3;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void process_chunk(const Win &W, uint32_t lq_arr, int
 // Every segment gets S2 slots of two consecutive chunks (S2 = ceil(largest chunk count / 2)), so slot f belongs to
 // segment f / S2: no lookup table and no prefix sum; slots past a segment's end run empty.  The caller's threads
 // cover slots f0, f0 + stride, ... (a warp: f0 = lane, stride 32; the whole CTA: f0 = tid, stride NT).
-template <bool BQ_HI>
+template <bool BQ_HI, int LAYOUT>
 __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint2 *desc,
                                               const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
                                               uint32_t &acc_sum, uint32_t f0, uint32_t stride) {
@@ -256,8 +257,8 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
 #endif
         const int e0 = (int)((d.y & 0x7ffu) + 16u * c) - (int)head;
         const uint32_t lq_arr = sLQ_s + (d.y >> 30) * (uint32_t)(LQ_SLAB * 4);
-        process_chunk<BQ_HI>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum);
-        if (rem > 16) process_chunk<BQ_HI>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum);
+        process_chunk<BQ_HI, LAYOUT>(W, lq_arr, e0, c == 0 ? head : 0u, (uint32_t)min(rem, 16), v0, sMaskLo, sMaskHi, t_low, acc_sum);
+        if (rem > 16) process_chunk<BQ_HI, LAYOUT>(W, lq_arr, e0 + 16, 0u, (uint32_t)min(rem - 16, 16), v1, sMaskLo, sMaskHi, t_low, acc_sum);
     }
 }
 
@@ -275,7 +276,7 @@ __device__ __forceinline__ void run_segments(const Win &W, uint32_t sLQ_s, uint3
     const uint32_t S2 = (__reduce_max_sync(FULL, nc) + 1u) >> 1;
     if (has) myDesc[__popc(bal & ((1u << lane) - 1u))] = pack_desc(sg, nc, slab);
     __syncwarp();
-    process_slots<BQ_HI>(W, sLQ_s, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)lane, 32u);
+    process_slots<BQ_HI, 2>(W, sLQ_s, __popc(bal), S2, myDesc, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)lane, 32u);
     __syncwarp();
 }
 
@@ -577,7 +578,9 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     {
         const uint32_t pool_n = ctl[1], pool_s2 = (ctl[2] + 1u) >> 1;
         if (tid < 3) sCtl[3 * ((round + 1) & 1) + tid] = tid == 0 ? rb1 : 0u;     // next round's controls (nobody reads them before the barrier below)
-        process_slots<BQ_HI>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)tid, (uint32_t)NT);
+        // the counter layout is a property of the window: one loop per layout keeps the test out of the per-chunk code
+        if (W.lq_packed) process_slots<BQ_HI, 1>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)tid, (uint32_t)NT);
+        else process_slots<BQ_HI, 0>(W, sLQ_s, pool_n, pool_s2, sPool, sRcp, sMaskLo, sMaskHi, t_low, acc_sum, (uint32_t)tid, (uint32_t)NT);
         // queued long reads: warps pull one at a time (balanced no matter which groups they came from)
         const uint32_t ncp = sCtl[16 + 2 * (round & 1)];
         if (tid >= 2 && tid < 4) sCtl[16 + 2 * ((round + 1) & 1) + (tid - 2)] = 0u;
