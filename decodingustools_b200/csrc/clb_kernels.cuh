@@ -7,11 +7,12 @@
 //   HistogramPlotter::process_coverage_ranges         .../utils/histogram_plotter.rs:74-102
 //
 // Design: one CTA owns a reference window of WREAL positions plus one halo position
-// to its left.  Warps autonomously pull 32 candidate reads at a time (coalesced column loads), walk the
-// CIGARs (lane-serial for short CIGARs, warp-cooperative prefix sums for long ones), and turn every
-// read / M-segment into two shared-memory difference-array updates instead of one update per base.
-// Base qualities are streamed once with 16-byte loads; only bases that FAIL the quality threshold touch
-// a per-position counter.  After a block scan the window is classified, run boundaries are compacted
+// to its left.  Warps take 32 candidate reads at a time (coalesced column loads), walk the CIGARs
+// (lane-serial for short CIGARs, warp-cooperative prefix sums for long ones), and turn every read /
+// M-segment into two shared-memory difference-array updates instead of one update per base.  The
+// M-segments go to a CTA-wide pool; after a barrier all threads stream their base qualities once with
+// 16-byte loads (prefetched into L2 at window start) and add one fail flag per byte to packed
+// per-position counters.  After a block scan the window is classified, run boundaries are compacted
 // into interval records, and counters / bins are reduced per CTA before a handful of global atomics.
 // No per-base array ever reaches HBM.
 #pragma once
@@ -38,7 +39,6 @@ constexpr int WN = NT * PPT;          // entries per window; entry 0 is the halo
 constexpr int WREAL = WN - 1;         // reference positions owned by one window
 constexpr int MAXSEG = 2;             // M-like segments a "simple" read may contribute
 constexpr int FAST_OPS = 6;           // CIGAR ops walked lane-serially; longer CIGARs go warp-cooperative
-constexpr int CHUNK_CAP = 352;        // 16-byte quality chunks mapped per warp round
 constexpr int NFIRST = 128;           // low-MAPQ threshold table entries cached in shared memory
 #ifndef CLB_KLQ
 #define CLB_KLQ 4
