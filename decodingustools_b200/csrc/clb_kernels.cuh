@@ -136,6 +136,16 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)
 __device__ __forceinline__ void red_shared(uint32_t saddr, uint32_t val) {
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(val) : "memory");
 }
+// single-lane shared atomics as plain instructions (the compiler wraps atomicAdd/atomicMax in warp-aggregation code
+// that is pure overhead when the caller has already elected one lane)
+__device__ __forceinline__ uint32_t atom_shared_add(uint32_t saddr, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_shared_max(uint32_t saddr, uint32_t val) {
+    asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(saddr), "r"(val) : "memory");
+}
 // add only when val != 0: one ISETP + one predicated ATOMS, no branch
 __device__ __forceinline__ void red_shared_nz(uint32_t saddr, uint32_t val) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" :: "r"(saddr), "r"(val) : "memory");
@@ -555,7 +565,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
             if (n0 + n1) {
                 const uint32_t mx = __reduce_max_sync(FULL, max(nc0, nc1));
                 uint32_t base = 0;
-                if (lane == 0) { base = atomicAdd(&ctl[1], n0 + n1); atomicMax(&ctl[2], mx); }
+                if (lane == 0) { base = atom_shared_add(smem_addr(&ctl[1]), n0 + n1); red_shared_max(smem_addr(&ctl[2]), mx); }
                 base = __shfl_sync(FULL, base, 0);
                 const uint32_t lt = (1u << lane) - 1u;
                 if (h0) sPool[base + __popc(bal0 & lt)] = pack_desc(sg0, nc0, slab);
@@ -567,7 +577,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         const uint32_t cmask = __ballot_sync(FULL, cplx);
         if (cmask) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&sCtl[16 + 2 * (round & 1)], (uint32_t)__popc(cmask));
+            if (lane == 0) base = atom_shared_add(smem_addr(&sCtl[16 + 2 * (round & 1)]), (uint32_t)__popc(cmask));
             base = __shfl_sync(FULL, base, 0);
             if (cplx) sCplx[(round & 1) * CPLX_CAP + base + __popc(cmask & ((1u << lane) - 1u))] = i0 + u * NT + lane;
         }
@@ -586,7 +596,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         if (tid >= 2 && tid < 4) sCtl[16 + 2 * ((round + 1) & 1) + (tid - 2)] = 0u;
         for (;;) {
             uint32_t qi = 0;
-            if (lane == 0) qi = atomicAdd(&sCtl[17 + 2 * (round & 1)], 1u);
+            if (lane == 0) qi = atom_shared_add(smem_addr(&sCtl[17 + 2 * (round & 1)]), 1u);
             qi = __shfl_sync(FULL, qi, 0);
             if (qi >= ncp) break;
             const uint32_t r = sCplx[(round & 1) * CPLX_CAP + qi];
@@ -689,12 +699,27 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         s = raw == 0 ? ST_NO_COVERAGE : s;
         s = ((nbits >> k) & 1u) ? ST_REF_N : s;
         stp |= (stp_t)s << (4 * k);
-        const uint32_t valid = (vmask >> k) & 1u;
-        cnt_pack += valid << (5 * s);
-        covered += (raw > 0 ? 1u : 0u) & valid;
-        if (WIDE) { sraw_w += valid ? raw : 0u; sqc_w += valid ? qc : 0u; }
-        else { sraw += valid ? raw : 0u; sqc += valid ? qc : 0u; }
-        b[k] = qc;                                                        // keep qc for the optional debug dump
+        cnt_pack += 1u << (5 * s);
+        covered += raw > 0 ? 1u : 0u;
+        if (WIDE) { sraw_w += raw; sqc_w += qc; }
+        else { sraw += raw; sqc += qc; }
+        b[k] = qc;                                                        // keep qc (entry 0 below, optional debug dump)
+    }
+    constexpr uint32_t ALL_ENTRIES = (1u << PPT) - 1u;
+    if (vmask != ALL_ENTRIES) {
+        // Few threads: the halo entry (thread 0) and entries past the region end were counted above; take them out again.
+        // Only entry 0 can carry depth (the halo is a real position); reads are clipped at the region end, so the
+        // entries past it have none.
+        uint32_t inv = ~vmask & ALL_ENTRIES;
+        if (inv & 1u) {
+            const uint32_t raw0 = WIDE ? a[0] : a[0] & 0xffffu;
+            covered -= raw0 > 0 ? 1u : 0u;
+            if (WIDE) { sraw_w -= raw0; sqc_w -= b[0]; } else { sraw -= raw0; sqc -= b[0]; }
+        }
+        while (inv) {
+            const int k = __ffs(inv) - 1; inv &= inv - 1;
+            cnt_pack -= 1u << (5 * ((uint32_t)(stp >> (4 * k)) & 15u));
+        }
     }
     if (DBG && P.dbg_raw) {                                                // per-base dump for the parity tests (own instantiation)
 #pragma unroll
