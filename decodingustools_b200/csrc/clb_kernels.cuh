@@ -686,24 +686,41 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     unsigned long long sraw_w = 0, sqc_w = 0;                              // deep windows: 32-bit partial sums could overflow
     const uint32_t min_dflm = P.min_depth_for_low_mapq, min_depth = P.min_depth;
     const uint32_t max_depth = P.max_depth ? P.max_depth : 0xffffffffu;   // max_depth == 0 disables EXCESSIVE_COVERAGE
+    // Two copies of the per-entry classification, chosen per thread: when none of the thread's entries is deeper than
+    // the shared-memory threshold table the lookup is a plain LDS; otherwise every entry may go to the global table
+    // (kept apart because those loads, predicated off, would still cost six issue slots per ordinary entry).
+    auto classify = [&](auto deep_tag) {
+        constexpr bool DEEP = decltype(deep_tag)::value;
 #pragma unroll
-    for (int k = 0; k < PPT; k++) {
-        const uint32_t raw = WIDE ? a[k] : a[k] & 0xffffu, low = WIDE ? lw[WIDE ? k : 0] : a[k] >> 16;
-        const uint32_t qc = b[k] - lqv[k];
-        uint32_t fst = sFirst[min(raw, (uint32_t)NFIRST - 1u)];
-        if (raw >= (uint32_t)NFIRST) fst = (WIDE && raw >= 65536u) ? first_low(raw, P.max_low_mapq_fraction) : P.first_tab[raw];   // deep positions only
-        const bool is_low = raw >= min_dflm && low >= fst;
-        uint32_t s = qc > max_depth ? ST_EXCESSIVE : ST_CALLABLE;
-        s = qc < min_depth ? ST_LOW_COVERAGE : s;
-        s = is_low ? ST_POOR_MAPQ : s;
-        s = raw == 0 ? ST_NO_COVERAGE : s;
-        s = ((nbits >> k) & 1u) ? ST_REF_N : s;
-        stp |= (stp_t)s << (4 * k);
-        cnt_pack += 1u << (5 * s);
-        covered += raw > 0 ? 1u : 0u;
-        if (WIDE) { sraw_w += raw; sqc_w += qc; }
-        else { sraw += raw; sqc += qc; }
-        b[k] = qc;                                                        // keep qc (entry 0 below, optional debug dump)
+        for (int k = 0; k < PPT; k++) {
+            const uint32_t raw = WIDE ? a[k] : a[k] & 0xffffu, low = WIDE ? lw[WIDE ? k : 0] : a[k] >> 16;
+            const uint32_t qc = b[k] - lqv[k];
+            uint32_t fst;
+            if (DEEP) {
+                fst = sFirst[min(raw, (uint32_t)NFIRST - 1u)];
+                if (raw >= (uint32_t)NFIRST) fst = (WIDE && raw >= 65536u) ? first_low(raw, P.max_low_mapq_fraction) : P.first_tab[raw];
+            } else {
+                fst = sFirst[raw];
+            }
+            const bool is_low = raw >= min_dflm && low >= fst;
+            uint32_t s = qc > max_depth ? ST_EXCESSIVE : ST_CALLABLE;
+            s = qc < min_depth ? ST_LOW_COVERAGE : s;
+            s = is_low ? ST_POOR_MAPQ : s;
+            s = raw == 0 ? ST_NO_COVERAGE : s;
+            s = ((nbits >> k) & 1u) ? ST_REF_N : s;
+            stp |= (stp_t)s << (4 * k);
+            cnt_pack += 1u << (5 * s);
+            covered += raw > 0 ? 1u : 0u;
+            if (WIDE) { sraw_w += raw; sqc_w += qc; }
+            else { sraw += raw; sqc += qc; }
+            b[k] = qc;                                                    // keep qc (entry 0 below, optional debug dump)
+        }
+    };
+    {
+        uint32_t deepest = 0;                                             // an upper bound of the thread's raw depths
+#pragma unroll
+        for (int k = 0; k < PPT; k++) deepest |= WIDE ? a[k] : a[k] & 0xffffu;
+        if (deepest < (uint32_t)NFIRST) classify(std::false_type{}); else classify(std::true_type{});
     }
     constexpr uint32_t ALL_ENTRIES = (1u << PPT) - 1u;
     if (vmask != ALL_ENTRIES) {
