@@ -323,7 +323,7 @@ def main():
         achieved = alg_bytes / (pileup_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE resident launch on the default workload, from the ncu --set full
         # capture summarised in profiles/r01_k_pileup_classify_resident_chr1.txt (same seed, same launch)
-        traffic = 8_916_798_000 if (args.scale == 1.0 and world == 1) else None
+        traffic = 8_922_642_000 if (args.scale == 1.0 and world == 1) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
