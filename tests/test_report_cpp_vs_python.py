@@ -1,0 +1,129 @@
+"""The C++ report writer the CLI uses (csrc/host/report_writer.hpp) against the Python mirror, on the CPU: platform
+inference and the BAM sampler on generated read names, the SVG plot on random bins, the HTML page byte for byte.
+The shim in tests/cpp/ is compiled with g++ on first use."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from decodingustools_b200 import bam_stats as bs
+from decodingustools_b200 import report
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PLATFORMS = [bs.ILLUMINA, bs.PACBIO, bs.NANOPORE, bs.MGI, bs.UNKNOWN]        # enum order of report_writer.hpp
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("shim") / "report_shim.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "cpp", "report_shim.cpp")], check=True)
+    L = C.CDLL(so)
+    L.shim_detect_platform.restype = C.c_int
+    for f in (L.shim_bam_stats, L.shim_svg, L.shim_html):
+        f.restype = C.c_size_t
+    L.shim_default_header.restype = C.c_char_p; L.shim_default_footer.restype = C.c_char_p
+    return L
+
+
+def _names(rng, n):
+    hexd = "0123456789abcdef"
+    out = []
+    for i in range(n):
+        kind = int(rng.integers(0, 9))
+        r = lambda a, b: int(rng.integers(a, b))
+        h = lambda k: "".join(hexd[r(0, 16)] for _ in range(k))
+        if kind == 0:
+            out.append(f"{'ADJKENMVFZ'[r(0, 10)]}{r(0, 99999):05d}:{r(1, 500)}:H{h(8).upper()}:{r(1, 5)}:{r(1101, 2678)}:{r(1, 30000)}:{r(1, 30000)}")
+        elif kind == 1:
+            out.append(f"m{['64', '54', '84', '99'][r(0, 4)]}{r(0, 999):03d}e_{r(200101, 251231)}_{r(0, 235959):06d}/{r(1, 10 ** 6)}/ccs")
+        elif kind == 2:
+            out.append(f"{h(8)}-{h(4)}-{h(4)}-{h(4)}-{h(12)}" + ("_extra" if r(0, 4) == 0 else ""))
+        elif kind == 3:
+            out.append(f"{['V300', 'E100', 'CL100', 'G400', 'G99', 'v300'][r(0, 6)]}{r(0, 10 ** 6):06d}L{r(1, 5)}C{r(1, 999):03d}R{r(1, 10 ** 8):08d}")
+        elif kind == 4:
+            out.append(f"{['V3', 'E1', 'CL1', 'G4', 'X9'][r(0, 5)]}{r(0, 999)}:{r(1, 9)}:{'LX'[r(0, 2)]}{r(1, 99):02d}:{r(1, 5)}:{r(1, 99)}:{r(1, 9999)}:{r(1, 9999)}:{r(0, 2)}")
+        elif kind == 5:
+            out.append(f"run{r(1, 50)}_ch{r(1, 512)}_read{r(1, 10 ** 5)}_strand{'_pass' * r(0, 3)}")
+        elif kind == 6:
+            out.append(f"chr{r(1, 23)}:q{r(0, 10 ** 6)}")
+        elif kind == 7:
+            out.append("".join(":-_/mLCRchread0189AVG"[r(0, 21)] for _ in range(r(1, 48))))
+        else:
+            out.append(f"{h(8)}-{h(4)}-{h(4)}-{h(4)}-{h(11)}Z")
+    return out
+
+
+def test_platform_detection_and_sampler_agree(shim):
+    rng = np.random.default_rng(99)
+    names = _names(rng, 4000)
+    for q in names:
+        assert PLATFORMS[shim.shim_detect_platform(q.encode())] == bs.detect_platform_from_qname(q), q
+    for trial in range(40):
+        k = int(rng.integers(1, 400))
+        # a dominant platform plus some noise, so that the most common instrument is well defined more often than not
+        pool = [q for q in names if bs.detect_platform_from_qname(q) == PLATFORMS[trial % 5]] or names
+        sub = [pool[int(rng.integers(0, len(pool)))] if rng.random() < 0.8 else names[int(rng.integers(0, len(names)))] for _ in range(k)]
+        flags = rng.choice(np.array([0, 1, 16, 0x100, 0x800, 0x900], np.uint16), k)
+        lens = rng.integers(0, 20000, k).astype(np.uint64)
+        cap = int(rng.integers(1, k + 50))
+        py = bs.BamStats(cap).collect(zip(sub, flags.tolist(), lens.tolist()))
+        blob = b"".join(q.encode() + b"\0" for q in sub)
+        rc, al, pr = C.c_uint64(), C.c_uint64(), C.c_int()
+        buf = C.create_string_buffer(256)
+        shim.shim_bam_stats(blob, flags.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), C.c_uint64(k), C.c_uint64(cap),
+                            C.byref(rc), C.byref(al), C.byref(pr), buf, C.c_size_t(256))
+        assert (rc.value, al.value, PLATFORMS[pr.value], buf.value.decode()) == (py.read_count, py.average_read_length(), py.primary_platform(), py.infer_platform())
+
+
+@pytest.mark.parametrize("length,stride,name", [(16_569, 83, "chrM"), (1_000, 10, "t<&>\"'"), (45_000_000, 22_500, "chr9"), (248_956_422, 124_479, "chr1"),
+                                                 (5_000, 124_479, "tiny"), (300_001, 1, "wide")])
+def test_svg_matches(shim, length, stride, name):
+    rng = np.random.default_rng(length % 9973)
+    n_bins = length // stride + 1
+    bins = np.zeros((3, n_bins), np.uint32)
+    for row, p in ((0, 0.7), (1, 0.3), (2, 0.1)):
+        m = rng.random(n_bins) < p
+        bins[row, m] = rng.integers(1, 2 * stride + 2, int(m.sum()))          # also past a full bar (quirk Q2 can do that)
+    expect = report.render_coverage_svg(name, length, stride, bins)
+    flat = np.ascontiguousarray(bins)
+    need = shim.shim_svg(name.encode(), C.c_uint32(length), C.c_uint32(stride), flat.ctypes.data_as(C.c_void_p), C.c_uint32(n_bins), None, C.c_size_t(0))
+    buf = C.create_string_buffer(need + 1)
+    shim.shim_svg(name.encode(), C.c_uint32(length), C.c_uint32(stride), flat.ctypes.data_as(C.c_void_p), C.c_uint32(n_bins), buf, C.c_size_t(need + 1))
+    assert buf.value.decode() == expect
+
+
+def test_html_matches(shim):
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n = int(rng.integers(0, 6))
+        f = lambda: float(rng.choice([0.0, 0.005, 0.125, 29.995, 99.995, 100.0, rng.random() * 100, rng.random() * 1e6]))
+        contigs = [dict(name=f"chr{i}", length=int(rng.integers(0, 10 ** 9)), unique_reads=int(rng.integers(0, 10 ** 7)), coverage_percent=f(), average_depth=f(),
+                        covered_bases=int(rng.integers(0, 10 ** 9)), total_bases=0, quality_stats=dict(average_mapq=f(), average_baseq=f(), q30_percentage=f()),
+                        state_distribution={k: int(rng.integers(0, 10 ** 9)) for k in ("ref_n", "callable", "no_coverage", "low_coverage", "excessive_coverage", "poor_mapping_quality")})
+                   for i in range(n)]
+        export = dict(summary=dict(aligner="BWA-MEM2", reference_build="GRCh38", sequencing_platform="PacBio Sequel II/IIe", read_length=int(rng.integers(0, 30000)),
+                                   total_bases=int(rng.integers(0, 4 * 10 ** 9)), callable_bases=int(rng.integers(0, 4 * 10 ** 9)), callable_percentage=f(),
+                                   average_depth=f(), contigs_analyzed=n),
+                      contigs=contigs, quality_metrics=dict(average_mapq=f(), average_baseq=f(), q30_percentage=f()), total_unique_reads=int(rng.integers(0, 10 ** 9)))
+        plots = {c["name"] for c in contigs if rng.random() < 0.5}
+        custom = trial % 2 == 1
+        head, foot = ("<h>\n", "</f>") if custom else (None, None)
+        expect = report.render_html_report(export, max_samples=10000 + trial, header_html=head, footer_html=foot, plot_exists=lambda p: p[:-len("_coverage.svg")] in plots)
+        s = export["summary"]
+        su = np.array([s["read_length"], export["total_unique_reads"], s["total_bases"], s["callable_bases"], n, 10000 + trial], np.uint64)
+        sd = np.array([s["callable_percentage"], s["average_depth"], export["quality_metrics"]["average_mapq"], export["quality_metrics"]["average_baseq"]], np.float64)
+        cu = np.array([[c["length"], c["unique_reads"], c["covered_bases"]] + [c["state_distribution"][k] for k in
+                       ("ref_n", "callable", "no_coverage", "low_coverage", "excessive_coverage", "poor_mapping_quality")] + [int(c["name"] in plots)] for c in contigs],
+                      np.uint64).reshape(n, 10)
+        cd = np.array([[c["coverage_percent"], c["average_depth"], c["quality_stats"]["average_mapq"], c["quality_stats"]["average_baseq"],
+                        c["quality_stats"]["q30_percentage"]] for c in contigs], np.float64).reshape(n, 5)
+        names = b"".join(c["name"].encode() + b"\0" for c in contigs) or b"\0"
+        args = [b"GRCh38", b"BWA-MEM2", b"PacBio Sequel II/IIe", su.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p), C.c_uint64(n), names,
+                cu.ctypes.data_as(C.c_void_p), cd.ctypes.data_as(C.c_void_p), head.encode() if custom else None, foot.encode() if custom else None]
+        need = shim.shim_html(*args, None, C.c_size_t(0))
+        buf = C.create_string_buffer(need + 1)
+        shim.shim_html(*args, buf, C.c_size_t(need + 1))
+        assert buf.value.decode() == expect
+    assert shim.shim_default_header().decode() == report.DEFAULT_REPORT_HEADER and shim.shim_default_footer().decode() == report.DEFAULT_REPORT_FOOTER
