@@ -11,14 +11,13 @@
 //   summary.json (written in the CWD)      src/main.rs:67-69, src/export/formats/coverage.rs (field order)
 //   detect_aligner / reference build       src/callable_loci/mod.rs:149-177, src/types.rs:100-147
 //   BamStats sampler, platform inference, SVG plots, HTML report: report_writer.hpp (citations there)
-// What rust-htslib did (BGZF inflate, BAM record decode, faidx) is done here: multi-threaded zlib inflate of BGZF blocks,
-// a sequential record scan (the file is coordinate sorted, so no .bai is needed) and an in-memory FASTA contig load.
+// What rust-htslib did (BGZF inflate, BAM record decode, faidx) is done in bam_reader.hpp: multi-threaded zlib inflate of BGZF
+// blocks, a sequential record scan (the file is coordinate sorted, so no .bai is needed) and an in-memory FASTA contig load.
 // The HTML page is wrapped in this tool's own header/footer unless --report-templates points at a reference checkout's
 // src/callable_loci/templates (then the page is what the reference writes, byte for byte).
 #include "../../../include/callable_loci_b200.h"
+#include "bam_reader.hpp"
 #include "report_writer.hpp"
-
-#include <zlib.h>
 
 #include <algorithm>
 #include <charconv>
@@ -27,153 +26,15 @@
 #include <fstream>
 #include <map>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
 
 namespace {
 
-[[noreturn]] void die(const std::string &m) { fprintf(stderr, "Error: %s\n", m.c_str()); exit(1); }
-
-// ------------------------------------------------------------------------------------------------ BGZF / BAM
-struct BamHeader { std::string text; std::vector<std::string> names; std::vector<uint32_t> lens; };
-
-struct BamRecordView {
-    int32_t tid, pos; uint8_t mapq; uint16_t flag; uint16_t n_cigar; int32_t l_seq;
-    const char *qname; uint32_t l_qname; const uint32_t *cigar; const uint8_t *qual;
-};
-
-class BgzfStream {
-  public:
-    BgzfStream(const std::string &path, unsigned threads) : threads_(std::max(1u, threads)) {
-        fp_ = fopen(path.c_str(), "rb");
-        if (!fp_) die("Failed to open BAM file: " + path);
-        cbuf_.reserve(kChunk + (1 << 17));
-    }
-    ~BgzfStream() { if (fp_) fclose(fp_); }
-    // Appends the next batch of inflated bytes to out; returns false at EOF.
-    bool next(std::vector<uint8_t> &out) {
-        if (eof_ && cbuf_.empty()) return false;
-        const size_t have = cbuf_.size();
-        cbuf_.resize(have + kChunk);
-        const size_t got = eof_ ? 0 : fread(cbuf_.data() + have, 1, kChunk, fp_);
-        cbuf_.resize(have + got);
-        if (got < kChunk) eof_ = true;
-        struct Blk { size_t off, clen, ulen, uoff; };
-        std::vector<Blk> blks; size_t o = 0, utotal = 0;
-        while (o + 18 <= cbuf_.size()) {
-            const uint8_t *p = cbuf_.data() + o;
-            if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) die("not a BGZF file (bad block header)");
-            const uint32_t xlen = p[10] | (p[11] << 8);
-            if (o + 12 + xlen > cbuf_.size()) break;
-            uint32_t bsize = 0; bool found = false;
-            for (uint32_t x = 0; x + 4 <= xlen;) {
-                const uint8_t *s = p + 12 + x; const uint32_t sl = s[2] | (s[3] << 8);
-                if (s[0] == 'B' && s[1] == 'C' && sl == 2) { bsize = (s[4] | (s[5] << 8)) + 1u; found = true; }
-                x += 4 + sl;
-            }
-            if (!found) die("BGZF block without BC field");
-            if (o + bsize > cbuf_.size()) break;
-            const uint8_t *tail = p + bsize - 4;
-            const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
-            blks.push_back({o + 12 + xlen, bsize - 12 - xlen - 8, isize, utotal});
-            utotal += isize; o += bsize;
-        }
-        if (blks.empty() && !cbuf_.empty() && eof_) die("truncated BGZF file");
-        const size_t base = out.size();
-        out.resize(base + utotal);
-        std::vector<std::thread> pool; std::vector<int> err(threads_, 0);
-        for (unsigned t = 0; t < threads_; t++)
-            pool.emplace_back([&, t] {
-                for (size_t i = t; i < blks.size(); i += threads_) {
-                    if (!blks[i].ulen) continue;
-                    z_stream zs; memset(&zs, 0, sizeof zs);
-                    if (inflateInit2(&zs, -15) != Z_OK) { err[t] = 1; return; }
-                    zs.next_in = cbuf_.data() + blks[i].off; zs.avail_in = (uInt)blks[i].clen;
-                    zs.next_out = out.data() + base + blks[i].uoff; zs.avail_out = (uInt)blks[i].ulen;
-                    const int rc = inflate(&zs, Z_FINISH);
-                    inflateEnd(&zs);
-                    if (rc != Z_STREAM_END || zs.avail_out != 0) { err[t] = 1; return; }
-                }
-            });
-        for (auto &th : pool) th.join();
-        for (int e : err) if (e) die("BGZF inflate failed");
-        cbuf_.erase(cbuf_.begin(), cbuf_.begin() + (long)o);
-        return true;
-    }
-
-  private:
-    static constexpr size_t kChunk = 64u << 20;
-    FILE *fp_ = nullptr; unsigned threads_; bool eof_ = false;
-    std::vector<uint8_t> cbuf_;
-};
-
-class BamReader {
-  public:
-    BamReader(const std::string &path, unsigned threads) : bz_(path, threads) {
-        need(12);
-        if (memcmp(cur(), "BAM\1", 4) != 0) die("Failed to open BAM file: not a BAM (CRAM is not supported by this host)");
-        const int32_t l_text = rd32(4); need(12 + (size_t)l_text);
-        hdr_.text.assign((const char *)cur() + 8, (size_t)l_text);
-        const int32_t n_ref = rd32(8 + l_text); off_ += 12 + (size_t)l_text;
-        for (int32_t i = 0; i < n_ref; i++) {
-            need(4); const int32_t l_name = rd32(0); need(8 + (size_t)l_name);
-            hdr_.names.emplace_back((const char *)cur() + 4, (size_t)std::max(0, l_name - 1));
-            hdr_.lens.push_back((uint32_t)rd32(4 + l_name));
-            off_ += 8 + (size_t)l_name;
-        }
-    }
-    const BamHeader &header() const { return hdr_; }
-    bool next(BamRecordView &r) {
-        if (!need(4)) return false;
-        const int32_t bs = rd32(0);
-        if (bs < 32 || !need(4 + (size_t)bs)) die("truncated BAM record");
-        const uint8_t *p = cur() + 4;
-        auto i32 = [&](int o) { int32_t v; memcpy(&v, p + o, 4); return v; };
-        auto u16 = [&](int o) { uint16_t v; memcpy(&v, p + o, 2); return v; };
-        r.tid = i32(0); r.pos = i32(4); r.l_qname = p[8]; r.mapq = p[9]; r.n_cigar = u16(12); r.flag = u16(14); r.l_seq = i32(16);
-        r.qname = (const char *)p + 32;
-        r.cigar = (const uint32_t *)(p + 32 + r.l_qname);
-        r.qual = p + 32 + r.l_qname + 4 * (size_t)r.n_cigar + ((size_t)r.l_seq + 1) / 2;
-        off_ += 4 + (size_t)bs;
-        return true;
-    }
-
-  private:
-    const uint8_t *cur() const { return buf_.data() + off_; }
-    int32_t rd32(size_t o) const { int32_t v; memcpy(&v, cur() + o, 4); return v; }
-    bool need(size_t n) {
-        while (buf_.size() - off_ < n) {
-            if (off_ > (32u << 20)) { buf_.erase(buf_.begin(), buf_.begin() + (long)off_); off_ = 0; }
-            if (!bz_.next(buf_)) return false;
-        }
-        return true;
-    }
-    BgzfStream bz_; std::vector<uint8_t> buf_; size_t off_ = 0; BamHeader hdr_;
-};
-
-// ------------------------------------------------------------------------------------------------ FASTA
-struct FaiEntry { uint64_t len, offset; uint32_t linebases, linewidth; };
-std::map<std::string, FaiEntry> load_fai(const std::string &fasta) {
-    std::map<std::string, FaiEntry> m;
-    std::ifstream in(fasta + ".fai");
-    if (!in) die("Failed to open reference: " + fasta + ".fai is missing (the reference also requires it, api/coverage.rs:73)");
-    std::string name; FaiEntry e;
-    while (in >> name >> e.len >> e.offset >> e.linebases >> e.linewidth) { m[name] = e; in.ignore(1 << 20, '\n'); }
-    return m;
-}
-std::vector<uint8_t> load_contig(const std::string &fasta, const FaiEntry &e) {
-    std::vector<uint8_t> seq; seq.reserve(e.len);
-    FILE *fp = fopen(fasta.c_str(), "rb");
-    if (!fp) die("Failed to open reference: " + fasta);
-    const uint64_t lines = e.linebases ? (e.len + e.linebases - 1) / e.linebases : 0;
-    std::vector<uint8_t> raw((size_t)(lines * e.linewidth + 16));
-    fseeko(fp, (off_t)e.offset, SEEK_SET);
-    const size_t got = fread(raw.data(), 1, raw.size(), fp);
-    fclose(fp);
-    for (size_t i = 0; i < got && seq.size() < e.len; i++) if (raw[i] != '\n' && raw[i] != '\r') seq.push_back(raw[i]);
-    return seq;
-}
+[[noreturn]] void die(const std::string &m) { throw std::runtime_error(m); }
+using namespace bamio;
 
 // ------------------------------------------------------------------------------------------------ report
 struct ContigStats {            // ContigProfiler + CallableProfiler::contig_counts
@@ -301,9 +162,7 @@ void usage() {
     exit(2);
 }
 
-}  // namespace
-
-int main(int argc, char **argv) {
+int run(int argc, char **argv) {
     if (argc < 3 || strcmp(argv[1], "coverage") != 0) usage();
     Options opt;
     for (int i = 2; i < argc; i++) {
@@ -483,4 +342,15 @@ int main(int argc, char **argv) {
     if (!fh) die("cannot create " + opt.summary);
     fwrite(html.data(), 1, html.size(), fh); fclose(fh);
     return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    try {
+        return run(argc, argv);
+    } catch (const std::exception &e) {      // every failure: message + exit code 1, the partially written BED stays behind
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
 }

@@ -29,9 +29,13 @@ def default_qname(contig: str, name_id: int) -> str:
     return f"{contig}:q{name_id}"
 
 
-def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN:bwa\n", qname_fn=default_qname):
+def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN:bwa\n", qname_fn=default_qname, block: int = 0xFF00,
+              cg_threshold: int = 65535, unmapped_tail: int = 0):
     """contigs: list of (name, length, ReadColumns) in tid order; QNAMEs are synthesised from name_id (mates share)
-    through qname_fn(contig, name_id)."""
+    through qname_fn(contig, name_id).  block: uncompressed bytes per BGZF block (small values make records straddle blocks).
+    Reads with more than cg_threshold CIGAR ops are stored the way htslib stores them: placeholder CIGAR <l_seq>S<ref_len>N plus
+    a CG:B,I tag (an NM:i tag and an RG:Z tag are put in front of it so the aux walk is exercised).  unmapped_tail appends that
+    many unmapped records (tid -1, pos -1, flag 4) after the last contig."""
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l, _ in contigs) + header_extra
     out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs)))
     for n, l, _ in contigs:
@@ -43,11 +47,21 @@ def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN
             c0, c1 = int(rc.cigar_off[i]), int(rc.cigar_off[i + 1])
             q0, q1 = int(rc.qual_off[i]), int(rc.qual_off[i + 1])
             lseq = q1 - q0
-            body = struct.pack("<iiBBHHHiiii", tid, int(rc.pos[i]), len(qn), int(rc.mapq[i]), 4680, c1 - c0, int(rc.flag[i]),
+            cigar = rc.cigar[c0:c1].astype("<u4")
+            aux = b""
+            if c1 - c0 > cg_threshold:
+                ref_len = int(sum(int(v) >> 4 for v in cigar if (int(v) & 15) in (0, 2, 3, 7, 8)))
+                aux = b"NMi" + struct.pack("<i", 3) + b"RGZgrp1\0" + b"CGBI" + struct.pack("<I", c1 - c0) + cigar.tobytes()
+                cigar = np.array([(lseq << 4) | 4, (ref_len << 4) | 3], dtype="<u4")
+            body = struct.pack("<iiBBHHHiiii", tid, int(rc.pos[i]), len(qn), int(rc.mapq[i]), 4680, len(cigar), int(rc.flag[i]),
                                lseq, -1, -1, 0)
-            body += qn + rc.cigar[c0:c1].astype("<u4").tobytes() + bytes((lseq + 1) // 2) + rc.qual[q0:q1].tobytes()
+            body += qn + cigar.tobytes() + bytes((lseq + 1) // 2) + rc.qual[q0:q1].tobytes() + aux
             out += struct.pack("<i", len(body)) + body
-    write_bgzf(path, bytes(out))
+    for i in range(unmapped_tail):
+        qn = f"unmapped{i}".encode() + b"\0"
+        body = struct.pack("<iiBBHHHiiii", -1, -1, len(qn), 0, 4680, 0, 4, 10, -1, -1, 0) + qn + bytes(5) + bytes([0xFF] * 10)
+        out += struct.pack("<i", len(body)) + body
+    write_bgzf(path, bytes(out), block)
 
 
 def write_fasta(path: str, contigs: Sequence, width: int = 60):

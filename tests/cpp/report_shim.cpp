@@ -49,3 +49,52 @@ const char *shim_default_header() { return report::default_header(); }
 const char *shim_default_footer() { return report::default_footer(); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ BAM / FASTA reader
+#include "../../decodingustools_b200/csrc/host/bam_reader.hpp"
+
+extern "C" {
+
+// Scans the whole file into caller-provided columns.  Returns 0, or 1 with a message in err.
+int shim_bam_scan(const char *path, unsigned threads, uint64_t cap_reads, uint64_t cap_cigar, uint64_t cap_qual, int32_t *tid, int32_t *pos,
+                  uint16_t *flag, uint8_t *mapq, uint32_t *cigar_off, uint32_t *cigar, uint64_t *qual_off, uint8_t *qual, char *names,
+                  size_t names_cap, char *hdr_text, size_t hdr_cap, char *ref_names, size_t ref_names_cap, uint32_t *ref_lens, uint32_t *n_ref,
+                  uint64_t *n_reads, char *err, size_t err_cap) {
+    try {
+        bamio::BamReader rd(path, threads);
+        const bamio::BamHeader &h = rd.header();
+        put(h.text, hdr_text, hdr_cap);
+        std::string rn; for (auto &n : h.names) { rn += n; rn.push_back('\n'); }
+        put(rn, ref_names, ref_names_cap);
+        *n_ref = (uint32_t)h.names.size();
+        for (size_t i = 0; i < h.lens.size(); i++) ref_lens[i] = h.lens[i];
+        bamio::BamRecordView r; uint64_t n = 0, nc = 0, nq = 0; size_t no = 0;
+        cigar_off[0] = 0; qual_off[0] = 0;
+        while (rd.next(r)) {
+            const uint64_t lq = (uint64_t)std::max(0, r.l_seq), ln = r.l_qname ? r.l_qname - 1 : 0;
+            if (n >= cap_reads || nc + r.n_cigar > cap_cigar || nq + lq > cap_qual || no + ln + 1 > names_cap) throw std::runtime_error("shim buffers too small");
+            tid[n] = r.tid; pos[n] = r.pos; flag[n] = r.flag; mapq[n] = r.mapq;
+            memcpy(cigar + nc, r.cigar, 4 * (size_t)r.n_cigar); nc += r.n_cigar; cigar_off[n + 1] = (uint32_t)nc;
+            memcpy(qual + nq, r.qual, lq); nq += lq; qual_off[n + 1] = nq;
+            memcpy(names + no, r.qname, ln); names[no + ln] = '\n'; no += ln + 1;
+            n++;
+        }
+        names[no < names_cap ? no : names_cap - 1] = 0;
+        *n_reads = n;
+        return 0;
+    } catch (const std::exception &e) { put(e.what(), err, err_cap); return 1; }
+}
+
+int64_t shim_load_contig(const char *fasta, const char *name, uint8_t *out, uint64_t cap, char *err, size_t err_cap) {
+    try {
+        const auto fai = bamio::load_fai(fasta);
+        const auto it = fai.find(name);
+        if (it == fai.end()) return -1;
+        const auto seq = bamio::load_contig(fasta, it->second);
+        if (seq.size() > cap) throw std::runtime_error("shim buffer too small");
+        memcpy(out, seq.data(), seq.size());
+        return (int64_t)seq.size();
+    } catch (const std::exception &e) { put(e.what(), err, err_cap); return -2; }
+}
+
+}  // extern "C"

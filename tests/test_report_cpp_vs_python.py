@@ -1,6 +1,7 @@
-"""The C++ report writer the CLI uses (csrc/host/report_writer.hpp) against the Python mirror, on the CPU: platform
-inference and the BAM sampler on generated read names, the SVG plot on random bins, the HTML page byte for byte.
-The shim in tests/cpp/ is compiled with g++ on first use."""
+"""The host-side C++ of the CLI on the CPU, through a g++-built shim (tests/cpp/): the report writer
+(csrc/host/report_writer.hpp) against the Python mirror -- platform inference and the BAM sampler on generated read
+names, the SVG plot on random bins, the HTML page byte for byte -- and the BGZF/BAM/FASTA reader (csrc/host/bam_reader.hpp)
+against files written by tests/bamio.py."""
 import ctypes as C
 import os
 import subprocess
@@ -18,12 +19,13 @@ PLATFORMS = [bs.ILLUMINA, bs.PACBIO, bs.NANOPORE, bs.MGI, bs.UNKNOWN]        # e
 @pytest.fixture(scope="module")
 def shim(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("shim") / "report_shim.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "cpp", "report_shim.cpp")], check=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "cpp", "report_shim.cpp"), "-lz", "-lpthread"], check=True)
     L = C.CDLL(so)
     L.shim_detect_platform.restype = C.c_int
     for f in (L.shim_bam_stats, L.shim_svg, L.shim_html):
         f.restype = C.c_size_t
     L.shim_default_header.restype = C.c_char_p; L.shim_default_footer.restype = C.c_char_p
+    L.shim_bam_scan.restype = C.c_int; L.shim_load_contig.restype = C.c_int64
     return L
 
 
@@ -127,3 +129,71 @@ def test_html_matches(shim):
         shim.shim_html(*args, buf, C.c_size_t(need + 1))
         assert buf.value.decode() == expect
     assert shim.shim_default_header().decode() == report.DEFAULT_REPORT_HEADER and shim.shim_default_footer().decode() == report.DEFAULT_REPORT_FOOTER
+
+
+def _scan(shim, path, threads, n_reads, n_cigar, n_qual, n_ref):
+    cap_r, cap_c, cap_q = n_reads + 8, n_cigar + 8, n_qual + 8
+    tid = np.zeros(cap_r, np.int32); pos = np.zeros(cap_r, np.int32); flag = np.zeros(cap_r, np.uint16); mapq = np.zeros(cap_r, np.uint8)
+    co = np.zeros(cap_r + 1, np.uint32); cg = np.zeros(cap_c, np.uint32); qo = np.zeros(cap_r + 1, np.uint64); ql = np.zeros(cap_q, np.uint8)
+    names = C.create_string_buffer(64 * cap_r); hdr = C.create_string_buffer(1 << 16); rn = C.create_string_buffer(1 << 12)
+    lens = np.zeros(max(n_ref, 1) + 4, np.uint32); nref = C.c_uint32(); n = C.c_uint64(); err = C.create_string_buffer(512)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = shim.shim_bam_scan(path.encode(), C.c_uint(threads), C.c_uint64(cap_r), C.c_uint64(cap_c), C.c_uint64(cap_q), p(tid), p(pos), p(flag), p(mapq),
+                            p(co), p(cg), p(qo), p(ql), names, C.c_size_t(len(names)), hdr, C.c_size_t(len(hdr)), rn, C.c_size_t(len(rn)), p(lens),
+                            C.byref(nref), C.byref(n), err, C.c_size_t(512))
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    k = n.value
+    return dict(n=k, tid=tid[:k], pos=pos[:k], flag=flag[:k], mapq=mapq[:k], cigar_off=co[:k + 1], cigar=cg[:int(co[k])], qual_off=qo[:k + 1],
+                qual=ql[:int(qo[k])], names=names.value.decode().split("\n")[:k], header=hdr.value.decode(), ref_names=rn.value.decode().split("\n")[:nref.value],
+                ref_lens=lens[:nref.value])
+
+
+@pytest.mark.parametrize("block,threads", [(0xFF00, 4), (777, 3), (97, 1)])
+def test_bam_reader_reads_back_what_was_written(shim, tmp_path, block, threads):
+    from tests import bamio
+    from tests.test_oracle_vs_naive import random_reads
+    rng = np.random.default_rng(block)
+    contigs = [("chrA", 5000, random_reads(rng, 5000, 300, max_len=80)), ("chrEmpty", 10, random_reads(rng, 10, 0)),
+               ("chrB", 900, random_reads(rng, 900, 120, max_len=40))]
+    path = str(tmp_path / "t.bam")
+    # CIGARs with more than 2 ops go through the CG-tag convention htslib uses past 65535 ops
+    bamio.write_bam(path, contigs, block=block, cg_threshold=2, unmapped_tail=5)
+    tot = sum(c[2].n for c in contigs)
+    got = _scan(shim, path, threads, tot + 5, sum(c[2].n_cigar for c in contigs), sum(c[2].n_qual for c in contigs) + 50, 3)
+    assert got["n"] == tot + 5 and got["ref_names"] == ["chrA", "chrEmpty", "chrB"] and got["ref_lens"].tolist() == [5000, 10, 900]
+    assert got["header"].startswith("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chrA\tLN:5000\n") and "@PG\tID:bwa" in got["header"]
+    o = 0
+    n_cg = 0
+    for tid, (name, _, rc) in enumerate(contigs):
+        k = rc.n
+        sl = slice(o, o + k)
+        assert (got["tid"][sl] == tid).all() and np.array_equal(got["pos"][sl], rc.pos) and np.array_equal(got["flag"][sl], rc.flag) and np.array_equal(got["mapq"][sl], rc.mapq)
+        c0, q0 = int(got["cigar_off"][o]), int(got["qual_off"][o])
+        assert np.array_equal(got["cigar_off"][o:o + k + 1] - c0, rc.cigar_off) and np.array_equal(got["cigar"][c0:c0 + rc.n_cigar], rc.cigar)   # real CIGARs, not placeholders
+        assert np.array_equal(got["qual_off"][o:o + k + 1] - q0, rc.qual_off) and np.array_equal(got["qual"][q0:q0 + rc.n_qual], rc.qual)
+        assert got["names"][sl] == [bamio.default_qname(name, int(i)) for i in (rc.name_id if rc.name_id is not None else range(k))]
+        n_cg += int((np.diff(rc.cigar_off.astype(np.int64)) > 2).sum())
+        o += k
+    assert n_cg > 20                                                       # the CG path was exercised
+    assert (got["tid"][o:] == -1).all() and (got["flag"][o:] == 4).all() and (got["qual"][-50:] == 0xFF).all() and got["names"][-1] == "unmapped4"
+
+
+def test_bam_reader_errors_and_fasta(shim, tmp_path):
+    from tests import bamio
+    bad = tmp_path / "bad.bam"; bad.write_bytes(b"this is not a BGZF file at all, not even close............")
+    with pytest.raises(RuntimeError, match="not a BGZF file"):
+        _scan(shim, str(bad), 2, 10, 10, 10, 1)
+    with pytest.raises(RuntimeError, match="Failed to open BAM file"):
+        _scan(shim, str(tmp_path / "missing.bam"), 2, 10, 10, 10, 1)
+    notbam = str(tmp_path / "notbam.bam"); bamio.write_bgzf(notbam, b"SAM\1" + bytes(64))
+    with pytest.raises(RuntimeError, match="not a BAM"):
+        _scan(shim, notbam, 2, 10, 10, 10, 1)
+    rng = np.random.default_rng(3)
+    seqs = [("chr1", bytes(rng.choice(list(b"ACGTNacgtn"), size=1234).tolist())), ("chrM", b"ACGT" * 17 + b"N"), ("empty", b"")]
+    fa = str(tmp_path / "r.fa"); bamio.write_fasta(fa, seqs, width=61)
+    for name, seq in seqs:
+        buf = np.zeros(len(seq) + 8, np.uint8); err = C.create_string_buffer(256)
+        n = shim.shim_load_contig(fa.encode(), name.encode(), buf.ctypes.data_as(C.c_void_p), C.c_uint64(len(buf)), err, C.c_size_t(256))
+        assert n == len(seq) and buf[:n].tobytes() == seq
+    assert shim.shim_load_contig(fa.encode(), b"chrZ", None, C.c_uint64(0), None, C.c_size_t(0)) == -1
