@@ -66,29 +66,8 @@ bool contig_less(const std::string &a, const std::string &b) {     // report.rs:
     return a.substr(sa) < b.substr(sb);
 }
 
-// serde_json / ryu formatting of an f64: shortest round-trip digits, ".0" for integers, exponent outside 1e-5..1e16
-std::string fmt_f64(double v) {
-    char buf[64];
-    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
-    std::string s(buf, res.ptr);                           // d[.ddd]e[+-]xx
-    const size_t epos = s.find('e');
-    std::string mant = s.substr(0, epos); const int exp10 = atoi(s.c_str() + epos + 1);
-    const bool neg = mant[0] == '-'; if (neg) mant.erase(0, 1);
-    std::string digits; for (char ch : mant) if (ch != '.') digits.push_back(ch);
-    const int nd = (int)digits.size(), kk = exp10 + 1;     // decimal point position relative to digits
-    std::string out;
-    if (v == 0) out = "0.0";
-    else if (nd <= kk && kk <= 16) { out = digits + std::string((size_t)(kk - nd), '0') + ".0"; }
-    else if (0 < kk && kk <= 16) { out = digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk); }
-    else if (-5 < kk && kk <= 0) { out = "0." + std::string((size_t)(-kk), '0') + digits; }
-    else { out = digits.substr(0, 1) + (nd > 1 ? "." + digits.substr(1) : "") + "e" + std::to_string(exp10); }
-    return (neg ? "-" : "") + out;
-}
-std::string jstr(const std::string &s) {
-    std::string o = "\"";
-    for (char ch : s) { if (ch == '"' || ch == '\\') { o += '\\'; o += ch; } else if (ch == '\n') o += "\\n"; else if (ch == '\t') o += "\\t"; else o += ch; }
-    return o + "\"";
-}
+using report::fmt_f64;
+using report::jstr;
 
 std::string detect_aligner(const std::string &header_text) {       // callable_loci/mod.rs:149-177
     std::string h = header_text; for (auto &c : h) c = (char)tolower((unsigned char)c);

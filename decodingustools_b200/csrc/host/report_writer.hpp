@@ -9,8 +9,10 @@
 // decodingustools_b200/bam_stats.py and report.py hold the same logic for Python callers; tests/test_cli_gpu.py compares
 // the two byte for byte.
 #pragma once
+#include <charconv>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -216,6 +218,31 @@ inline std::string render_coverage_svg(const std::string &contig, uint32_t conti
     }
     o += "</svg>\n";
     return o;
+}
+
+// ------------------------------------------------------------------------------------------------ summary.json scalars
+// serde_json / ryu formatting of an f64: shortest round-trip digits, ".0" for integers, exponent outside 1e-5..1e16
+inline std::string fmt_f64(double v) {
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    std::string s(buf, res.ptr);                           // d[.ddd]e[+-]xx
+    const size_t epos = s.find('e');
+    std::string mant = s.substr(0, epos); const int exp10 = atoi(s.c_str() + epos + 1);
+    const bool neg = mant[0] == '-'; if (neg) mant.erase(0, 1);
+    std::string digits; for (char ch : mant) if (ch != '.') digits.push_back(ch);
+    const int nd = (int)digits.size(), kk = exp10 + 1;     // decimal point position relative to digits
+    std::string out;
+    if (v == 0) out = "0.0";
+    else if (nd <= kk && kk <= 16) { out = digits + std::string((size_t)(kk - nd), '0') + ".0"; }
+    else if (0 < kk && kk <= 16) { out = digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk); }
+    else if (-5 < kk && kk <= 0) { out = "0." + std::string((size_t)(-kk), '0') + digits; }
+    else { out = digits.substr(0, 1) + (nd > 1 ? "." + digits.substr(1) : "") + "e" + std::to_string(exp10); }
+    return (neg ? "-" : "") + out;
+}
+inline std::string jstr(const std::string &s) {
+    std::string o = "\"";
+    for (char ch : s) { if (ch == '"' || ch == '\\') { o += '\\'; o += ch; } else if (ch == '\n') o += "\\n"; else if (ch == '\t') o += "\\t"; else o += ch; }
+    return o + "\"";
 }
 
 // ------------------------------------------------------------------------------------------------ HTML report

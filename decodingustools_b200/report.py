@@ -265,3 +265,65 @@ def render_html_report(export: dict, max_samples: int = 10000, header_html: str 
     h.append("</div></div>")
     h.append(DEFAULT_REPORT_FOOTER if footer_html is None else footer_html)
     return "".join(h)
+
+
+# ------------------------------------------------------------------------------------------------ summary.json
+def format_f64(v: float) -> str:
+    """An f64 the way serde_json prints it (ryu's pretty format: shortest round-trip digits, ".0" on integers, plain
+    decimals for 1e-5 <= |v| < 1e16, otherwise d.ddde[-]x without a plus sign or padding)."""
+    if v == 0:
+        return "-0.0" if str(v).startswith("-") else "0.0"
+    r = repr(float(v))
+    neg = r.startswith("-")
+    if neg:
+        r = r[1:]
+    mant, _, ex = r.partition("e")
+    ip, _, fp = mant.partition(".")
+    digits = (ip + fp).lstrip("0")
+    exp10 = int(ex or 0) + len(ip) - (len(ip + fp) - len((ip + fp).lstrip("0")))    # value = 0.digits * 10^exp10
+    digits = digits.rstrip("0") or "0"
+    nd, kk = len(digits), exp10                                # kk = position of the decimal point relative to the digits
+    if nd <= kk <= 16:
+        out = digits + "0" * (kk - nd) + ".0"
+    elif 0 < kk <= 16:
+        out = digits[:kk] + "." + digits[kk:]
+    elif -5 < kk <= 0:
+        out = "0." + "0" * (-kk) + digits
+    else:
+        out = digits[0] + ("." + digits[1:] if nd > 1 else "") + "e" + str(kk - 1)
+    return ("-" if neg else "") + out
+
+
+def _json_str(s: str) -> str:
+    return '"' + s.replace("\\", "\\\\").replace('"', '\\"').replace("\n", "\\n").replace("\t", "\\t") + '"'
+
+
+def render_summary_json(export: dict, bed_file: str, summary_html: str, coverage_plots) -> str:
+    """summary.json as main.rs:67-69 writes it (serde_json::to_writer_pretty of CoverageOutput: two-space indent, struct
+    field order of export/formats/coverage.rs and api/coverage.rs:134-145, no trailing newline)."""
+    s, qm = export["summary"], export["quality_metrics"]
+
+    def contig(c):
+        q, d = c["quality_stats"], c["state_distribution"]
+        return ("      {\n"
+                f'        "name": {_json_str(c["name"])},\n        "length": {c["length"]},\n        "unique_reads": {c["unique_reads"]},\n'
+                f'        "coverage_percent": {format_f64(c["coverage_percent"])},\n        "average_depth": {format_f64(c["average_depth"])},\n'
+                f'        "covered_bases": {c["covered_bases"]},\n        "total_bases": {c["total_bases"]},\n        "quality_stats": {{\n'
+                f'          "average_mapq": {format_f64(q["average_mapq"])},\n          "average_baseq": {format_f64(q["average_baseq"])},\n'
+                f'          "q30_percentage": {format_f64(q["q30_percentage"])}\n        }},\n        "state_distribution": {{\n'
+                f'          "ref_n": {d["ref_n"]},\n          "callable": {d["callable"]},\n          "no_coverage": {d["no_coverage"]},\n'
+                f'          "low_coverage": {d["low_coverage"]},\n          "excessive_coverage": {d["excessive_coverage"]},\n'
+                f'          "poor_mapping_quality": {d["poor_mapping_quality"]}\n        }}\n      }}')
+
+    contigs = ",\n".join(contig(c) for c in export["contigs"])
+    plots = ",\n".join("      " + _json_str(p) for p in coverage_plots)
+    return ("{\n  \"export\": {\n    \"summary\": {\n"
+            f'      "aligner": {_json_str(s["aligner"])},\n      "reference_build": {_json_str(s["reference_build"])},\n'
+            f'      "sequencing_platform": {_json_str(s["sequencing_platform"])},\n      "read_length": {s["read_length"]},\n'
+            f'      "total_bases": {s["total_bases"]},\n      "callable_bases": {s["callable_bases"]},\n'
+            f'      "callable_percentage": {format_f64(s["callable_percentage"])},\n      "average_depth": {format_f64(s["average_depth"])},\n'
+            f'      "contigs_analyzed": {s["contigs_analyzed"]}\n    }},\n    "contigs": [' + (f"\n{contigs}\n    " if contigs else "") + "],\n"
+            f'    "quality_metrics": {{\n      "average_mapq": {format_f64(qm["average_mapq"])},\n      "average_baseq": {format_f64(qm["average_baseq"])},\n'
+            f'      "q30_percentage": {format_f64(qm["q30_percentage"])}\n    }},\n    "total_unique_reads": {export["total_unique_reads"]}\n  }},\n'
+            f'  "files": {{\n    "bed_file": {_json_str(bed_file)},\n    "summary_html": {_json_str(summary_html)},\n    "coverage_plots": ['
+            + (f"\n{plots}\n    " if plots else "") + "]\n  }\n}")

@@ -98,3 +98,6 @@ int64_t shim_load_contig(const char *fasta, const char *name, uint8_t *out, uint
 }
 
 }  // extern "C"
+
+extern "C" size_t shim_fmt_f64(double v, char *out, size_t cap) { return put(report::fmt_f64(v), out, cap); }
+extern "C" size_t shim_jstr(const char *s, char *out, size_t cap) { return put(report::jstr(s), out, cap); }

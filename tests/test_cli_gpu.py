@@ -111,6 +111,7 @@ def test_cli_report_outputs_match_the_python_mirror(tmp_path):
                 assert path.read_text() == report.render_coverage_svg(oc.name, oc.length, oc.stride, oc.bins), oc.name
         assert js["export"]["summary"]["sequencing_platform"] == "NovaSeq" and js["export"]["summary"]["read_length"] == 150
         assert js["files"]["coverage_plots"] == [f"{oc.name}_coverage.svg" for oc in o.contigs if oc.bins is not None]
+        assert (tmp_path / "summary.json").read_text() == report.render_summary_json(js["export"], "out.bed", "summary.html", js["files"]["coverage_plots"])
         html = (tmp_path / "summary.html").read_text()
         assert html == report.render_html_report(js["export"], header_html=head, footer_html=foot, plot_exists=lambda q: (tmp_path / q).exists())
         assert html.count("<figure") == sum(oc.bins is not None for oc in o.contigs) > 0

@@ -26,6 +26,8 @@ def shim(tmp_path_factory):
         f.restype = C.c_size_t
     L.shim_default_header.restype = C.c_char_p; L.shim_default_footer.restype = C.c_char_p
     L.shim_bam_scan.restype = C.c_int; L.shim_load_contig.restype = C.c_int64
+    L.shim_fmt_f64.restype = C.c_size_t; L.shim_fmt_f64.argtypes = [C.c_double, C.c_char_p, C.c_size_t]
+    L.shim_jstr.restype = C.c_size_t
     return L
 
 
@@ -197,3 +199,39 @@ def test_bam_reader_errors_and_fasta(shim, tmp_path):
         n = shim.shim_load_contig(fa.encode(), name.encode(), buf.ctypes.data_as(C.c_void_p), C.c_uint64(len(buf)), err, C.c_size_t(256))
         assert n == len(seq) and buf[:n].tobytes() == seq
     assert shim.shim_load_contig(fa.encode(), b"chrZ", None, C.c_uint64(0), None, C.c_size_t(0)) == -1
+
+
+def test_json_scalars_match_and_follow_serde_json(shim):
+    """f64 -> text is where summary.json could silently differ from the reference's (serde_json + ryu): known answers for
+    the format switches, then C++ against Python on random doubles of every magnitude."""
+    known = {0.0: "0.0", 1.0: "1.0", 100.0: "100.0", 0.1: "0.1", 99.5: "99.5", 1e15: "1000000000000000.0", 1e16: "1e16", 1.5e16: "1.5e16",
+             1e-5: "0.00001", 1.234e-5: "0.00001234", 9.99e-6: "9.99e-6", 1e-7: "1e-7", 0.30000000000000004: "0.30000000000000004",
+             5e-324: "5e-324", 1.7976931348623157e308: "1.7976931348623157e308", 12345.678: "12345.678", -3.25: "-3.25", 41.13333333333333: "41.13333333333333"}
+    buf = C.create_string_buffer(64)
+    for v, text in known.items():
+        shim.shim_fmt_f64(v, buf, 64)
+        assert buf.value.decode() == text == report.format_f64(v), v
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([rng.random(3000) * 10.0 ** rng.integers(-12, 20, 3000), rng.integers(0, 10 ** 9, 500) / 1e3,
+                           np.frombuffer(rng.bytes(8 * 3000), dtype=np.float64), rng.integers(0, 2 ** 53, 500).astype(np.float64)])
+    for v in vals[np.isfinite(vals)]:
+        shim.shim_fmt_f64(float(v), buf, 64)
+        t = buf.value.decode()
+        assert t == report.format_f64(float(v)) and float(t) == float(v), v
+    for text in ["chr1", 'we"ird\\name', "tab\there", "line\nbreak", ""]:
+        need = shim.shim_jstr(text.encode(), None, C.c_size_t(0))
+        b2 = C.create_string_buffer(need + 1)
+        shim.shim_jstr(text.encode(), b2, C.c_size_t(need + 1))
+        assert b2.value.decode() == report._json_str(text)
+
+
+def test_summary_json_layout():
+    import json
+    from tests.test_report_outputs import _export
+    ex = _export()
+    text = report.render_summary_json(ex, "out dir/callable.bed", "summary.html", ["chr1_coverage.svg", "chrM_coverage.svg"])
+    assert json.loads(text) == dict(export=ex, files=dict(bed_file="out dir/callable.bed", summary_html="summary.html",
+                                                         coverage_plots=["chr1_coverage.svg", "chrM_coverage.svg"]))
+    assert text.startswith('{\n  "export": {\n    "summary": {\n      "aligner": "BWA",\n') and text.endswith('"chrM_coverage.svg"\n    ]\n  }\n}')
+    empty = dict(ex, contigs=[])
+    assert '"contigs": [],' in report.render_summary_json(empty, "b", "h", []) and '"coverage_plots": []\n' in report.render_summary_json(empty, "b", "h", [])
