@@ -39,15 +39,23 @@ class BgzfStream {
         if (!fp_) die("Failed to open BAM file: " + path);
         cbuf_.reserve(kChunk + (1 << 17));
     }
+    // Continue at a compressed file offset (the upper 48 bits of a BAI virtual offset).  Reads start small and grow again,
+    // so that fetching a small contig does not inflate 64 MB of its neighbours.
+    void seek(uint64_t coffset) {
+        if (fseeko(fp_, (off_t)coffset, SEEK_SET) != 0) die("seek failed in BAM file");
+        cbuf_.clear(); eof_ = false; chunk_ = 1u << 20;
+    }
     ~BgzfStream() { if (fp_) fclose(fp_); }
     // Appends the next batch of inflated bytes to out; returns false at EOF.
     bool next(std::vector<uint8_t> &out) {
         if (eof_ && cbuf_.empty()) return false;
         const size_t have = cbuf_.size();
-        cbuf_.resize(have + kChunk);
-        const size_t got = eof_ ? 0 : fread(cbuf_.data() + have, 1, kChunk, fp_);
+        const size_t want = chunk_;
+        chunk_ = std::min(kChunk, chunk_ * 4);
+        cbuf_.resize(have + want);
+        const size_t got = eof_ ? 0 : fread(cbuf_.data() + have, 1, want, fp_);
         cbuf_.resize(have + got);
-        if (got < kChunk) eof_ = true;
+        if (got < want) eof_ = true;
         struct Blk { size_t off, clen, ulen, uoff; };
         std::vector<Blk> blks; size_t o = 0, utotal = 0;
         while (o + 18 <= cbuf_.size()) {
@@ -93,6 +101,7 @@ class BgzfStream {
 
   private:
     static constexpr size_t kChunk = 64u << 20;
+    size_t chunk_ = kChunk;
     FILE *fp_ = nullptr; unsigned threads_; bool eof_ = false;
     std::vector<uint8_t> cbuf_;
 };
@@ -113,6 +122,14 @@ class BamReader {
         }
     }
     const BamHeader &header() const { return hdr_; }
+    // Continue at a BAI virtual offset (compressed block offset << 16 | offset inside the inflated block).
+    void seek(uint64_t voffset) {
+        bz_.seek(voffset >> 16);
+        buf_.clear(); off_ = 0;
+        const size_t skip = (size_t)(voffset & 0xffffu);
+        if (skip && !need(skip)) die("BAI offset past the end of the BAM file");
+        off_ = skip;
+    }
     bool next(BamRecordView &r) {
         if (!need(4)) return false;
         const int32_t bs = rd32(0);
@@ -160,6 +177,37 @@ class BamReader {
     }
     BgzfStream bz_; std::vector<uint8_t> buf_; size_t off_ = 0; BamHeader hdr_;
 };
+
+// ------------------------------------------------------------------------------------------------ BAI
+// What `bam.fetch((tid, 0, len))` needs from the index (mod.rs:54): where the first record of a contig starts.
+// first[tid] = smallest chunk start over the contig's bins (UINT64_MAX: no records).  Looks for <bam>.bai, then <stem>.bai.
+struct BaiIndex { std::vector<uint64_t> first; };
+inline bool load_bai(const std::string &bam_path, BaiIndex &out) {
+    std::ifstream in(bam_path + ".bai", std::ios::binary);
+    if (!in && bam_path.size() > 4 && bam_path.compare(bam_path.size() - 4, 4, ".bam") == 0) in.open(bam_path.substr(0, bam_path.size() - 4) + ".bai", std::ios::binary);
+    if (!in) return false;
+    std::vector<uint8_t> b((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    size_t o = 0;
+    auto u32 = [&]() { if (o + 4 > b.size()) die("truncated BAI index"); uint32_t v; memcpy(&v, b.data() + o, 4); o += 4; return v; };
+    auto u64 = [&]() { if (o + 8 > b.size()) die("truncated BAI index"); uint64_t v; memcpy(&v, b.data() + o, 8); o += 8; return v; };
+    if (b.size() < 8 || memcmp(b.data(), "BAI\1", 4) != 0) die("not a BAI index");
+    o = 4;
+    const uint32_t n_ref = u32();
+    out.first.assign(n_ref, UINT64_MAX);
+    for (uint32_t r = 0; r < n_ref; r++) {
+        const uint32_t n_bin = u32();
+        for (uint32_t i = 0; i < n_bin; i++) {
+            const uint32_t bin = u32(), n_chunk = u32();
+            for (uint32_t c = 0; c < n_chunk; c++) {
+                const uint64_t beg = u64(); u64();
+                if (bin != 37450u) out.first[r] = std::min(out.first[r], beg);     // 37450: the metadata pseudo-bin
+            }
+        }
+        const uint32_t n_intv = u32();
+        for (uint32_t i = 0; i < n_intv; i++) u64();
+    }
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------------ FASTA
 struct FaiEntry { uint64_t len, offset; uint32_t linebases, linewidth; };

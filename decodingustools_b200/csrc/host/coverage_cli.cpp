@@ -12,7 +12,7 @@
 //   detect_aligner / reference build       src/callable_loci/mod.rs:149-177, src/types.rs:100-147
 //   BamStats sampler, platform inference, SVG plots, HTML report: report_writer.hpp (citations there)
 // What rust-htslib did (BGZF inflate, BAM record decode, faidx) is done in bam_reader.hpp: multi-threaded zlib inflate of BGZF
-// blocks, a sequential record scan (the file is coordinate sorted, so no .bai is needed) and an in-memory FASTA contig load.
+// blocks, a record scan (sequential, or per selected contig through the .bai when there is one) and an in-memory FASTA contig load.
 // The HTML page is wrapped in this tool's own header/footer unless --report-templates points at a reference checkout's
 // src/callable_loci/templates (then the page is what the reference writes, byte for byte).
 #include "../../../include/callable_loci_b200.h"
@@ -192,26 +192,32 @@ int run(int argc, char **argv) {
     if (!bed) die("Failed to create CallableProfiler: cannot create " + opt.out_bed);
     auto check = [&](int rc, const char *what) { if (rc != 0) die(std::string("Error processing contig: ") + what + ": " + clb_last_error(ctx)); };
 
-    // BamStats: first 10 000 records, primary alignments only (bam_stats.rs:60-76)
+    // BamStats: its own pass over the first 10 000 records of the file, primary alignments only (bam_stats.rs:44-76)
     report::BamStats bs;
-    auto sample = [&](const BamRecordView &r) {
-        if (!bs.full()) bs.add_record(std::string(r.qname, r.l_qname ? r.l_qname - 1 : 0), r.flag, (uint64_t)std::max(0, r.l_seq));
-    };
+    {
+        BamReader head(opt.bam, std::min(opt.threads, 4u));
+        BamRecordView r;
+        while (!bs.full() && head.next(r)) bs.add_record(std::string(r.qname, r.l_qname ? r.l_qname - 1 : 0), r.flag, (uint64_t)std::max(0, r.l_seq));
+    }
+    // With a contig selection and a .bai next to the BAM the reader jumps to each contig (what bam.fetch does, mod.rs:54);
+    // otherwise the coordinate-sorted file is scanned once from the start.
+    BaiIndex bai;
+    const bool indexed = opt.have_contigs && load_bai(opt.bam, bai) && bai.first.size() == H.names.size();
     // coverage plots land next to the BED file (callable_profiler.rs:24-27,80-83)
     const size_t slash = opt.out_bed.find_last_of('/');
     const std::string out_dir = slash == std::string::npos ? "" : opt.out_bed.substr(0, slash + 1);
 
-    Columns cols; BamRecordView rec; bool have = bam.next(rec);
+    Columns cols; BamRecordView rec; bool have = indexed ? false : bam.next(rec);
     const uint32_t maxcnt = opt.o.max_depth > 0 ? opt.o.max_depth : 500;
     for (auto &kv : stats) {                                           // ascending tid (api/coverage.rs:229-235)
         const int32_t tid = kv.first; ContigStats &st = kv.second;
         cols.clear();
-        while (have && (rec.tid < tid && rec.tid >= 0)) {               // records of contigs that were not selected
-            sample(rec);
-            have = bam.next(rec);
+        if (indexed) {
+            have = bai.first[(size_t)tid] != UINT64_MAX;
+            if (have) { bam.seek(bai.first[(size_t)tid]); have = bam.next(rec); }
         }
+        while (have && (rec.tid < tid && rec.tid >= 0)) have = bam.next(rec);   // records of contigs that were not selected
         while (have && rec.tid == tid) {
-            sample(rec);
             cols.push(rec);
             have = bam.next(rec);
         }
@@ -251,7 +257,6 @@ int run(int argc, char **argv) {
         fprintf(stderr, "%s: %llu admitted reads, %llu cells, %.2f ms on device\n", st.name.c_str(), (unsigned long long)adm.n_reads,
                 (unsigned long long)res.summed_coverage, res.kernel_ms);
     }
-    while (have && !bs.full()) { sample(rec); have = bam.next(rec); }
     if (clb_bed_writer_close(bed) != 0) die("failed to write " + opt.out_bed);
     clb_destroy(ctx);
 

@@ -18,11 +18,59 @@ def _bgzf_block(data: bytes) -> bytes:
     return hdr + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data))
 
 
-def write_bgzf(path: str, payload: bytes, block: int = 0xFF00):
+def write_bgzf(path: str, payload: bytes, block: int = 0xFF00) -> List[int]:
+    """Returns the file offset of every block (the EOF marker block included)."""
+    starts = []
     with open(path, "wb") as f:
         for o in range(0, len(payload), block):
+            starts.append(f.tell())
             f.write(_bgzf_block(payload[o:o + block]))
+        starts.append(f.tell())
         f.write(_bgzf_block(b""))                # EOF marker
+    return starts
+
+
+def _reg2bin(beg: int, end: int) -> int:
+    end -= 1
+    for shift, level in ((14, 15), (17, 12), (20, 9), (23, 6), (26, 3)):
+        if beg >> shift == end >> shift:
+            return ((1 << level) - 1) // 7 + (beg >> shift)
+    return 0
+
+
+def write_bai(path: str, n_ref: int, records, block_starts: List[int], block: int, n_no_coor: int = 0):
+    """records: (tid, beg, end, payload_offset_start, payload_offset_end) of every mapped record in file order."""
+    voff = lambda o: (block_starts[o // block] << 16) | (o % block)
+    out = bytearray(b"BAI\1" + struct.pack("<i", n_ref))
+    for tid in range(n_ref):
+        bins, linear, first, last, n = {}, {}, None, None, 0
+        for t, beg, end, o0, o1 in records:
+            if t != tid:
+                continue
+            v0, v1 = voff(o0), voff(o1)
+            chunks = bins.setdefault(_reg2bin(beg, max(end, beg + 1)), [])
+            if chunks and chunks[-1][1] == v0:
+                chunks[-1][1] = v1                               # consecutive records of one bin share a chunk
+            else:
+                chunks.append([v0, v1])
+            for w in range(beg >> 14, (max(end, beg + 1) - 1 >> 14) + 1):
+                linear[w] = min(linear.get(w, v0), v0)
+            first = v0 if first is None else first
+            last = v1; n += 1
+        if n:
+            bins[37450] = [[first, last], [n, 0]]                # metadata pseudo-bin
+        out += struct.pack("<i", len(bins))
+        for b, chunks in bins.items():
+            out += struct.pack("<Ii", b, len(chunks)) + b"".join(struct.pack("<QQ", c0, c1) for c0, c1 in chunks)
+        n_intv = max(linear) + 1 if linear else 0
+        out += struct.pack("<i", n_intv)
+        prev = 0
+        for w in range(n_intv):
+            prev = linear.get(w, prev)
+            out += struct.pack("<Q", prev)
+    out += struct.pack("<Q", n_no_coor)
+    with open(path, "wb") as f:
+        f.write(out)
 
 
 def default_qname(contig: str, name_id: int) -> str:
@@ -30,17 +78,18 @@ def default_qname(contig: str, name_id: int) -> str:
 
 
 def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN:bwa\n", qname_fn=default_qname, block: int = 0xFF00,
-              cg_threshold: int = 65535, unmapped_tail: int = 0):
+              cg_threshold: int = 65535, unmapped_tail: int = 0, index: bool = False):
     """contigs: list of (name, length, ReadColumns) in tid order; QNAMEs are synthesised from name_id (mates share)
     through qname_fn(contig, name_id).  block: uncompressed bytes per BGZF block (small values make records straddle blocks).
     Reads with more than cg_threshold CIGAR ops are stored the way htslib stores them: placeholder CIGAR <l_seq>S<ref_len>N plus
     a CG:B,I tag (an NM:i tag and an RG:Z tag are put in front of it so the aux walk is exercised).  unmapped_tail appends that
-    many unmapped records (tid -1, pos -1, flag 4) after the last contig."""
+    many unmapped records (tid -1, pos -1, flag 4) after the last contig.  index: also write path + ".bai"."""
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l, _ in contigs) + header_extra
     out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs)))
     for n, l, _ in contigs:
         nb = n.encode() + b"\0"
         out += struct.pack("<i", len(nb)) + nb + struct.pack("<i", l)
+    recs = []
     for tid, (name, _, rc) in enumerate(contigs):
         for i in range(rc.n):
             qn = qname_fn(name, int(rc.name_id[i]) if rc.name_id is not None else i).encode() + b"\0"
@@ -56,12 +105,16 @@ def write_bam(path: str, contigs: Sequence, header_extra: str = "@PG\tID:bwa\tPN
             body = struct.pack("<iiBBHHHiiii", tid, int(rc.pos[i]), len(qn), int(rc.mapq[i]), 4680, len(cigar), int(rc.flag[i]),
                                lseq, -1, -1, 0)
             body += qn + cigar.tobytes() + bytes((lseq + 1) // 2) + rc.qual[q0:q1].tobytes() + aux
+            span = int(sum(int(v) >> 4 for v in rc.cigar[c0:c1] if (int(v) & 15) in (0, 2, 3, 7, 8)))
+            recs.append((tid, int(rc.pos[i]), int(rc.pos[i]) + span, len(out), len(out) + 4 + len(body)))
             out += struct.pack("<i", len(body)) + body
     for i in range(unmapped_tail):
         qn = f"unmapped{i}".encode() + b"\0"
         body = struct.pack("<iiBBHHHiiii", -1, -1, len(qn), 0, 4680, 0, 4, 10, -1, -1, 0) + qn + bytes(5) + bytes([0xFF] * 10)
         out += struct.pack("<i", len(body)) + body
-    write_bgzf(path, bytes(out), block)
+    starts = write_bgzf(path, bytes(out), block)
+    if index:
+        write_bai(path + ".bai", len(contigs), recs, starts, block, unmapped_tail)
 
 
 def write_fasta(path: str, contigs: Sequence, width: int = 60):

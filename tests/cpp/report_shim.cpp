@@ -101,3 +101,19 @@ int64_t shim_load_contig(const char *fasta, const char *name, uint8_t *out, uint
 
 extern "C" size_t shim_fmt_f64(double v, char *out, size_t cap) { return put(report::fmt_f64(v), out, cap); }
 extern "C" size_t shim_jstr(const char *s, char *out, size_t cap) { return put(report::jstr(s), out, cap); }
+
+// Records of one contig through the BAI index (seek + scan until the tid changes): returns the record count and the
+// sum of their positions, -1 without an index, -2 on error.
+extern "C" int64_t shim_bam_fetch_tid(const char *path, int32_t tid, int64_t *pos_sum, uint64_t *first_voffset, char *err, size_t err_cap) {
+    try {
+        bamio::BaiIndex bai;
+        if (!bamio::load_bai(path, bai)) return -1;
+        bamio::BamReader rd(path, 2);
+        *first_voffset = bai.first.at((size_t)tid);
+        if (*first_voffset == UINT64_MAX) return 0;
+        rd.seek(*first_voffset);
+        bamio::BamRecordView r; int64_t n = 0; *pos_sum = 0;
+        while (rd.next(r) && r.tid == tid) { n++; *pos_sum += r.pos; }
+        return n;
+    } catch (const std::exception &e) { put(e.what(), err, err_cap); return -2; }
+}

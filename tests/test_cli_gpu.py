@@ -17,10 +17,12 @@ pytestmark = pytest.mark.gpu
 CLI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "decodingustools_b200", "decodingus-tools-b200")
 
 
-def _run(tmp_path, contigs, extra_args=(), fasta_contigs=None):
+def _run(tmp_path, contigs, extra_args=(), fasta_contigs=None, index=False):
     """contigs: (name, tid, length, ref, reads)."""
     bam = str(tmp_path / "in.bam"); fa = str(tmp_path / "ref.fa")
-    bamio.write_bam(bam, [(n, l, r) for n, _, l, _, r in contigs])
+    if os.path.exists(bam + ".bai"):
+        os.remove(bam + ".bai")
+    bamio.write_bam(bam, [(n, l, r) for n, _, l, _, r in contigs], index=index, block=4096 if index else 0xFF00)
     bamio.write_fasta(fa, fasta_contigs if fasta_contigs is not None else [(n, ref) for n, _, _, ref, _ in contigs])
     p = subprocess.run([CLI, "coverage", bam, "-r", fa, "-o", str(tmp_path / "out.bed"), *extra_args], cwd=tmp_path,
                        capture_output=True, text=True, timeout=600)
@@ -59,8 +61,11 @@ def test_cli_matches_oracle_on_a_small_genome(tmp_path):
     assert js["files"]["bed_file"].endswith("out.bed") and '"coverage_percent": ' in raw
     # -L keeps tid order and the largest-contig rule only sees the selected contigs
     sel = [contigs[1], contigs[2]]
-    bed, js, _ = _run(tmp_path, contigs, ["-L", "chrM", "-L", "chr2"])
+    bed, js, raw = _run(tmp_path, contigs, ["-L", "chrM", "-L", "chr2"])
     _check(sel, CallableOptions(), bed, js)
+    # with a .bai next to the BAM the reader jumps to the selected contigs: same files
+    bed_i, js_i, raw_i = _run(tmp_path, contigs, ["-L", "chrM", "-L", "chr2"], index=True)
+    assert bed_i == bed and raw_i == raw
 
 
 def test_cli_flags_weird_cigars_and_short_reference(tmp_path):

@@ -28,6 +28,7 @@ def shim(tmp_path_factory):
     L.shim_bam_scan.restype = C.c_int; L.shim_load_contig.restype = C.c_int64
     L.shim_fmt_f64.restype = C.c_size_t; L.shim_fmt_f64.argtypes = [C.c_double, C.c_char_p, C.c_size_t]
     L.shim_jstr.restype = C.c_size_t
+    L.shim_bam_fetch_tid.restype = C.c_int64
     return L
 
 
@@ -235,3 +236,29 @@ def test_summary_json_layout():
     assert text.startswith('{\n  "export": {\n    "summary": {\n      "aligner": "BWA",\n') and text.endswith('"chrM_coverage.svg"\n    ]\n  }\n}')
     empty = dict(ex, contigs=[])
     assert '"contigs": [],' in report.render_summary_json(empty, "b", "h", []) and '"coverage_plots": []\n' in report.render_summary_json(empty, "b", "h", [])
+
+
+@pytest.mark.parametrize("block", [0xFF00, 300])
+def test_bai_fetch_jumps_to_each_contig(shim, tmp_path, block):
+    from tests import bamio
+    from tests.test_oracle_vs_naive import random_reads
+    rng = np.random.default_rng(block + 1)
+    contigs = [("chrA", 40_000, random_reads(rng, 40_000, 500, max_len=90)), ("chrEmpty", 500, random_reads(rng, 500, 0)),
+               ("chrB", 70_000, random_reads(rng, 70_000, 800, max_len=60)), ("chrC", 300, random_reads(rng, 300, 40, max_len=30))]
+    path = str(tmp_path / "i.bam")
+    bamio.write_bam(path, contigs, block=block, unmapped_tail=3, index=True)
+    err = C.create_string_buffer(256)
+    for tid, (_, _, rc) in enumerate(contigs):
+        ps, fv = C.c_int64(), C.c_uint64()
+        n = shim.shim_bam_fetch_tid(path.encode(), C.c_int32(tid), C.byref(ps), C.byref(fv), err, C.c_size_t(256))
+        assert n == rc.n, err.value
+        if rc.n:
+            assert ps.value == int(rc.pos.astype(np.int64).sum())
+        else:
+            assert fv.value == 2 ** 64 - 1
+    os.rename(path + ".bai", str(tmp_path / "i.bai"))                       # <stem>.bai is found as well
+    assert shim.shim_bam_fetch_tid(path.encode(), C.c_int32(2), C.byref(ps), C.byref(fv), err, C.c_size_t(256)) == contigs[2][2].n
+    os.remove(str(tmp_path / "i.bai"))
+    assert shim.shim_bam_fetch_tid(path.encode(), C.c_int32(0), C.byref(ps), C.byref(fv), err, C.c_size_t(256)) == -1
+    (tmp_path / "i.bam.bai").write_bytes(b"BAI\1\4\0\0\0\1\0")
+    assert shim.shim_bam_fetch_tid(path.encode(), C.c_int32(0), C.byref(ps), C.byref(fv), err, C.c_size_t(256)) == -2 and b"truncated BAI" in err.value
