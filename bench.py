@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the contig (1.0 = chr1, 248.96 Mbp)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-mbp", type=float, default=16.0, help="oracle sample for cpu_baseline (Mbp of the contig)")
+    ap.add_argument("--cpu-sample-mbp", type=float, default=48.0, help="oracle sample for cpu_baseline (Mbp of the contig; about 12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch-reads", type=int, default=4_000_000, help="column-batch size of the e2e leg")
     return ap.parse_args()
