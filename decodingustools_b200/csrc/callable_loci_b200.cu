@@ -195,9 +195,10 @@ int launch_compaction(clb_ctx *ctx) {
     const uint32_t warps_per_block = 8;
     k_gather_intervals<<<(ctx->n_windows + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->s_compute>>>(
         (const unsigned long long *)ctx->rec.p, (const uint2 *)ctx->win_tab.p, (const uint32_t *)ctx->win_out.p, ctx->n_windows,
-        (IntervalOut *)ctx->intervals.p);
+        (IntervalOut *)ctx->intervals.p, (const uint32_t *)ctx->misc.p + M_ERR);
     k_fill_ends<<<std::max(1, ctx->n_sm * 4), 256, 0, ctx->s_compute>>>((IntervalOut *)ctx->intervals.p,
-                                                                       (const uint32_t *)ctx->misc.p + M_NTOTAL, ctx->region_end);
+                                                                       (const uint32_t *)ctx->misc.p + M_NTOTAL, ctx->region_end,
+                                                                       (const uint32_t *)ctx->misc.p + M_ERR);
     k_pack_stats<<<1, 32, 0, ctx->s_compute>>>((const unsigned long long *)ctx->stats_padded.p, (unsigned long long *)ctx->counters.p);
     ctx->launches += 4;
     CU(cudaGetLastError());

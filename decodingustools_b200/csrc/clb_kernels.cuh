@@ -1030,11 +1030,13 @@ __global__ void k_scan_windows(const uint2 *win_tab, uint32_t n_w, uint32_t *win
 }
 
 // one warp per window: move its records to their sorted place (start/state/soft; end filled next)
+// (nothing to gather when the record buffer overflowed: the records past its capacity were never written and the
+// interval array is just as small; the host grows both and re-runs the contig)
 __global__ void k_gather_intervals(const unsigned long long *rec, const uint2 *win_tab, const uint32_t *win_out, uint32_t n_w,
-                                   IntervalOut *out) {
+                                   IntervalOut *out, const uint32_t *err) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= n_w) return;
+    if (w >= n_w || (*err & ERR_REC_OVERFLOW)) return;
     const uint2 t = win_tab[w];
     const uint32_t o = win_out[w];
     for (uint32_t i = lane; i < t.y; i += 32) {
@@ -1044,7 +1046,8 @@ __global__ void k_gather_intervals(const unsigned long long *rec, const uint2 *w
     }
 }
 
-__global__ void k_fill_ends(IntervalOut *out, const uint32_t *n_total, uint32_t region_end) {
+__global__ void k_fill_ends(IntervalOut *out, const uint32_t *n_total, uint32_t region_end, const uint32_t *err) {
+    if (*err & ERR_REC_OVERFLOW) return;
     const uint32_t n = *n_total;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         out[i].end = (i + 1 < n) ? out[i + 1].start : region_end;

@@ -297,3 +297,15 @@ def test_more_than_65535_reads_in_one_window(same_start):
         o, _ = assert_parity([("chrD", 0, length, ref, both)], opt)
         if opt.max_depth:
             assert o.contigs[0].n_admitted > 65_535 and (not same_start or max(o.contigs[0].counts) > 0)
+
+
+def test_more_runs_than_the_first_record_buffer_holds(ctx_default):
+    """A reference that alternates N / non-N at every base yields one BED run per base: far more than the initial
+    boundary-record capacity (a quarter of the region), so the contig is re-run with a grown buffer."""
+    length = 400_001
+    ref = (b"AN" * (length // 2 + 1))[:length]
+    reads = ReadColumns.from_records([(p, 0, 60, "100M", 35, f"r{p}_{k}") for p in range(1000, 200_000, 37) for k in range(2)])
+    o, g = assert_parity([("alt", 0, length, ref, reads)], CallableOptions(), ctx_default)
+    assert o.bed().count(b"\n") == length                                   # every run is one base long
+    # the grown buffer is kept: a second contig through the same context still agrees
+    assert_parity([("alt2", 0, 70_000, ref[:70_000], ReadColumns.empty())], CallableOptions(), ctx_default)
