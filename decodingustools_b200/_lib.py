@@ -43,9 +43,9 @@ class ContigResult(C.Structure):
                 ("summed_baseq", C.c_uint64), ("summed_mapq", C.c_uint64), ("quality_bases", C.c_uint64),
                 ("n_intervals", C.c_uint64), ("intervals", C.POINTER(Interval)), ("n_bins", C.c_uint32),
                 ("stride", C.c_uint32), ("bins", C.POINTER(C.c_uint32)), ("region_start", C.c_uint32),
-                ("region_end", C.c_uint32), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("pileup_ms", C.c_float), ("_pad0", C.c_float),
+                ("region_end", C.c_uint32), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("pileup_ms", C.c_float), ("fast_ms", C.c_float),
                 ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("gpu_launches", C.c_uint32), ("_pad", C.c_uint32)]
+                ("d2h_bytes", C.c_uint64), ("gpu_launches", C.c_uint32), ("general_windows", C.c_uint32)]
 
 
 # every symbol include/callable_loci_b200.h declares (tests check that the library exports all of them)

@@ -56,6 +56,8 @@ class ContigDeviceResult:
     h2d_bytes: int = 0
     d2h_bytes: int = 0
     gpu_launches: int = 0
+    fast_ms: float = 0.0
+    general_windows: int = 0
 
 
 def _result(res: _lib.ContigResult, copy_intervals: bool = True) -> ContigDeviceResult:
@@ -69,7 +71,8 @@ def _result(res: _lib.ContigResult, copy_intervals: bool = True) -> ContigDevice
     return ContigDeviceResult(np.array(list(res.state_counts), dtype=np.uint64), int(res.n_covered_bases),
                               int(res.summed_coverage), int(res.summed_baseq), int(res.summed_mapq), int(res.quality_bases),
                               iv, bins, int(res.stride), int(res.region_start), int(res.region_end), float(res.kernel_ms),
-                              float(res.h2d_ms), float(res.pileup_ms), int(res.h2d_bytes), int(res.d2h_bytes), int(res.gpu_launches))
+                              float(res.h2d_ms), float(res.pileup_ms), int(res.h2d_bytes), int(res.d2h_bytes), int(res.gpu_launches),
+                              float(res.fast_ms), int(res.general_windows))
 
 
 class CallableLociContext:

@@ -6,12 +6,14 @@
 // Reference seam replaced: callable_loci::process_single_contig, /root/reference/src/callable_loci/mod.rs:44-147.
 #include "../../include/callable_loci_b200.h"
 #include "clb_kernels.cuh"
+#include "clb_fast.cuh"
 
 #include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +41,7 @@ struct clb_ctx {
     std::vector<EvPair> ev_kernel, ev_h2d;
     uint32_t *d_first_tab = nullptr;
     int max_ctas_per_sm = 0, n_sm = 0;
+    bool force_general = false;         // CLB_FORCE_GENERAL=1: every window through the general kernel (A/B measurements, tests)
 
     // contig state
     bool in_contig = false, finished = false;
@@ -54,6 +57,7 @@ struct clb_ctx {
     DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end, cigar_ckpt;
     DevBuf nmask, ref_ascii;
     DevBuf stats_padded, counters, rec, win_tab, win_r, win_q, win_out, deep_list, intervals, misc;
+    DevBuf win_g, gen_list, blk_tot;
     DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state, timing;
     uint32_t rec_cap = 0;
     bool dbg = false;
@@ -69,8 +73,9 @@ struct clb_ctx {
     uint64_t n_intervals = 0;
 };
 
-// misc layout (uint32): [0] record cursor, [1] error bits, [2] n_total intervals, [3] max ref span
-enum { M_CURSOR = 0, M_ERR = 1, M_NTOTAL = 2, M_DEEP = 3, M_MAXSPAN = 4, M_WORDS = 8 };
+// misc layout (uint32): record cursor, error bits, n_total intervals, deep-window count, general-queue count / tickets taken
+// (these six are reset per run), then the maximum reference span
+enum { M_CURSOR = 0, M_ERR = 1, M_NTOTAL = 2, M_DEEP = 3, M_GEN_COUNT = 4, M_GEN_TAKEN = 5, M_RESET_WORDS = 6, M_MAXSPAN = 7, M_WORDS = 8 };
 
 namespace {
 
@@ -140,6 +145,9 @@ KParams make_params(clb_ctx *c) {
     P.win_tab = (uint2 *)c->win_tab.p;
     P.err = (uint32_t *)c->misc.p + M_ERR;
     P.deep_count = (uint32_t *)c->misc.p + M_DEEP; P.deep_list = (uint32_t *)c->deep_list.p;
+    P.win_g = (const uint2 *)c->win_g.p; P.gen_list = (uint32_t *)c->gen_list.p;
+    P.gen_count = (uint32_t *)c->misc.p + M_GEN_COUNT; P.gen_taken = (uint32_t *)c->misc.p + M_GEN_TAKEN;
+    P.max_span = (const uint32_t *)c->misc.p + M_MAXSPAN;
     P.max_low_mapq_fraction = c->opt.max_low_mapq_fraction;
     P.timing = (long long *)c->timing.p;
     if (c->dbg) {
@@ -149,24 +157,40 @@ KParams make_params(clb_ctx *c) {
     return P;
 }
 
-// K0 + K1 for windows [w0, w1) on the compute stream
-int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup = nullptr) {
+// window ranges + classes, the fast kernel (one CTA per window) and the general kernel (persistent CTAs over the
+// queue of windows the other two handed over) for windows [w0, w1) on the compute stream
+int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup = nullptr, EvPair *time_fast = nullptr) {
     if (w1 <= w0) return CLB_OK;
     const uint32_t n = w1 - w0;
+    const bool all_general = ctx->force_general || ctx->long_mode;
     k_window_ranges<<<(n + 127) / 128, 128, 0, ctx->s_compute>>>(
         (const int32_t *)ctx->pos.p, (uint32_t)ctx->n_reads, ctx->region_start, ctx->region_end,
-        (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p, ctx->stride,
-        (uint4 *)ctx->win_r.p, (ulonglong2 *)ctx->win_q.p);
+        (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p, (const uint32_t *)ctx->cigar_off.p, ctx->stride,
+        (uint4 *)ctx->win_r.p, (ulonglong2 *)ctx->win_q.p, all_general ? 1u : 0u, (uint2 *)ctx->win_g.p,
+        (uint32_t *)ctx->gen_list.p, (uint32_t *)ctx->misc.p + M_GEN_COUNT);
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
     const bool hi = ctx->opt.min_base_quality >= 128;
-    if (ctx->dbg) {                                      // per-base dump requested (parity tests): separate instantiation
-        if (hi) k_pileup_classify<true, true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
-        else k_pileup_classify<false, true><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+    if (!all_general) {
+        if (time_fast) CU(cudaEventRecord(time_fast->a, ctx->s_compute));
+        if (ctx->dbg) {                                  // per-base dump requested (parity tests): separate instantiation
+            if (hi) k_pileup_fast<true, true><<<n, NT, F_SMEM, ctx->s_compute>>>(P);
+            else k_pileup_fast<false, true><<<n, NT, F_SMEM, ctx->s_compute>>>(P);
+        } else {
+            if (hi) k_pileup_fast<true, false><<<n, NT, F_SMEM, ctx->s_compute>>>(P);
+            else k_pileup_fast<false, false><<<n, NT, F_SMEM, ctx->s_compute>>>(P);
+        }
+        if (time_fast) CU(cudaEventRecord(time_fast->b, ctx->s_compute));
+        ctx->launches += 1;
+    }
+    const uint32_t g = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * std::max(1, ctx->max_ctas_per_sm), all_general ? n : 0xffffffffu);
+    if (ctx->dbg) {
+        if (hi) k_pileup_general<true, true><<<g, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+        else k_pileup_general<false, true><<<g, NT, SMEM_BYTES, ctx->s_compute>>>(P);
     } else {
-        if (hi) k_pileup_classify<true, false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
-        else k_pileup_classify<false, false><<<n, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+        if (hi) k_pileup_general<true, false><<<g, NT, SMEM_BYTES, ctx->s_compute>>>(P);
+        else k_pileup_general<false, false><<<g, NT, SMEM_BYTES, ctx->s_compute>>>(P);
     }
     if (time_pileup) CU(cudaEventRecord(time_pileup->b, ctx->s_compute));
     ctx->launches += 2;
@@ -177,30 +201,38 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
 int reset_accumulators(clb_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->stats_padded.p, 0, (size_t)N_STATS * STAT_STRIDE * 8, ctx->s_compute));
     CU(cudaMemsetAsync(ctx->counters.p, 0, ((size_t)N_STATS + 3 * (size_t)ctx->n_bins) * 8, ctx->s_compute));
-    CU(cudaMemsetAsync((uint32_t *)ctx->misc.p + M_CURSOR, 0, 4 * sizeof(uint32_t), ctx->s_compute));   // cursor, err, n_total, deep windows
+    CU(cudaMemsetAsync((uint32_t *)ctx->misc.p + M_CURSOR, 0, M_RESET_WORDS * sizeof(uint32_t), ctx->s_compute));   // cursor, err, n_total, deep windows, general queue
     return CLB_OK;
 }
 
 int launch_compaction(clb_ctx *ctx) {
     if (ctx->n_windows == 0) return CLB_OK;
     {
-        // windows with more than 65535 candidate reads were queued by the main pass (normally none)
+        // windows with more than 65535 candidate reads were queued by the general kernel (normally none)
         const KParams P = make_params(ctx);
-        if (ctx->opt.min_base_quality >= 128) k_pileup_classify_deep<true><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
-        else k_pileup_classify_deep<false><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+        const bool hi = ctx->opt.min_base_quality >= 128;
+        if (ctx->dbg) {
+            if (hi) k_pileup_classify_deep<true, true><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+            else k_pileup_classify_deep<false, true><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+        } else {
+            if (hi) k_pileup_classify_deep<true, false><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+            else k_pileup_classify_deep<false, false><<<ctx->n_sm, NT, SMEM_BYTES_DEEP, ctx->s_compute>>>(P);
+        }
         ctx->launches += 1;
     }
-    k_scan_windows<<<1, 1024, 0, ctx->s_compute>>>((const uint2 *)ctx->win_tab.p, ctx->n_windows, (uint32_t *)ctx->win_out.p,
-                                                  (uint32_t *)ctx->misc.p + M_NTOTAL);
+    const uint32_t n_blk = (ctx->n_windows + 1023) / 1024;
+    k_scan_windows_local<<<n_blk, 1024, 0, ctx->s_compute>>>((const uint2 *)ctx->win_tab.p, ctx->n_windows, (uint32_t *)ctx->win_out.p,
+                                                            (uint32_t *)ctx->blk_tot.p);
+    k_scan_blocks<<<1, 1024, 0, ctx->s_compute>>>((uint32_t *)ctx->blk_tot.p, n_blk, (uint32_t *)ctx->misc.p + M_NTOTAL);
     const uint32_t warps_per_block = 8;
     k_gather_intervals<<<(ctx->n_windows + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->s_compute>>>(
-        (const unsigned long long *)ctx->rec.p, (const uint2 *)ctx->win_tab.p, (const uint32_t *)ctx->win_out.p, ctx->n_windows,
-        (IntervalOut *)ctx->intervals.p, (const uint32_t *)ctx->misc.p + M_ERR);
+        (const unsigned long long *)ctx->rec.p, (const uint2 *)ctx->win_tab.p, (const uint32_t *)ctx->win_out.p,
+        (const uint32_t *)ctx->blk_tot.p, ctx->n_windows, (IntervalOut *)ctx->intervals.p, (const uint32_t *)ctx->misc.p + M_ERR);
     k_fill_ends<<<std::max(1, ctx->n_sm * 4), 256, 0, ctx->s_compute>>>((IntervalOut *)ctx->intervals.p,
                                                                        (const uint32_t *)ctx->misc.p + M_NTOTAL, ctx->region_end,
                                                                        (const uint32_t *)ctx->misc.p + M_ERR);
     k_pack_stats<<<1, 32, 0, ctx->s_compute>>>((const unsigned long long *)ctx->stats_padded.p, (unsigned long long *)ctx->counters.p);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CU(cudaGetLastError());
     return CLB_OK;
 }
@@ -213,6 +245,9 @@ int alloc_outputs(clb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->win_q, nw * sizeof(ulonglong2), false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_out, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->deep_list, nw * 4, false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->gen_list, nw * 4, false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->win_g, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->blk_tot, ((nw + 1023) / 1024 + 1) * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->rec, (size_t)ctx->rec_cap * 8, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->intervals, (size_t)ctx->rec_cap * sizeof(IntervalOut), false, ctx->s_compute))) return rc;
     return CLB_OK;
@@ -267,19 +302,22 @@ int fetch_result(clb_ctx *ctx, clb_contig_result *out) {
         out->kernel_ms = kms; out->h2d_ms = hms;
         out->h2d_bytes = ctx->h2d_bytes; out->d2h_bytes = ctx->d2h_bytes;
         out->gpu_launches = ctx->launches;
+        out->general_windows = ctx->h_misc[M_GEN_COUNT];
     }
     return CLB_OK;
 }
 
 // all kernels of the resident contig, from scratch (used for re-runs and record-buffer growth)
-int run_all_resident(clb_ctx *ctx, float *ms, float *pileup_ms = nullptr) {
+int run_all_resident(clb_ctx *ctx, float *ms, float *pileup_ms = nullptr, float *fast_ms = nullptr) {
     int rc;
-    EvPair ep, ek;
+    EvPair ep, ek, ef;
     if ((rc = get_events(ctx, ep))) return rc;
     if ((rc = get_events(ctx, ek))) return rc;
+    if ((rc = get_events(ctx, ef))) return rc;
     CU(cudaEventRecord(ep.a, ctx->s_compute));
     if ((rc = reset_accumulators(ctx))) return rc;
-    if ((rc = launch_windows(ctx, 0, ctx->n_windows, &ek))) return rc;
+    const bool fast_runs = !(ctx->force_general || ctx->long_mode) && ctx->n_windows;
+    if ((rc = launch_windows(ctx, 0, ctx->n_windows, &ek, &ef))) return rc;
     if ((rc = launch_compaction(ctx))) return rc;
     CU(cudaEventRecord(ep.b, ctx->s_compute));
     CU(cudaStreamSynchronize(ctx->s_compute));
@@ -287,7 +325,8 @@ int run_all_resident(clb_ctx *ctx, float *ms, float *pileup_ms = nullptr) {
     CU(cudaEventElapsedTime(&t, ep.a, ep.b));
     if (ms) *ms = t;
     if (pileup_ms) { *pileup_ms = 0; if (ctx->n_windows) CU(cudaEventElapsedTime(pileup_ms, ek.a, ek.b)); }
-    ctx->ev_pool.push_back(ep); ctx->ev_pool.push_back(ek);
+    if (fast_ms) { *fast_ms = 0; if (fast_runs) CU(cudaEventElapsedTime(fast_ms, ef.a, ef.b)); }
+    ctx->ev_pool.push_back(ep); ctx->ev_pool.push_back(ek); ctx->ev_pool.push_back(ef);
     return CLB_OK;
 }
 
@@ -324,15 +363,21 @@ clb_ctx *clb_create(int device, const clb_options *opt, char *err, size_t err_le
     if ((e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return bail("cudaStreamCreate", e); }
     ctx->s_compute = ctx->s_own;
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
-    if ((e = cudaFuncSetAttribute(k_pileup_classify<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify_deep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_DEEP)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pileup_classify_deep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_DEEP)) != cudaSuccess) {
-        clb_destroy(ctx); return bail("cudaFuncSetAttribute(smem)", e);
+    {
+        const char *fg = getenv("CLB_FORCE_GENERAL");
+        ctx->force_general = fg && fg[0] && fg[0] != '0';
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_classify<false, false>, NT, SMEM_BYTES);
+#define CLB_SMEM_ATTR(kernel, bytes) \
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))) != cudaSuccess) { \
+        clb_destroy(ctx); return bail("cudaFuncSetAttribute(" #kernel ")", e); }
+    CLB_SMEM_ATTR((k_pileup_general<false, false>), SMEM_BYTES) CLB_SMEM_ATTR((k_pileup_general<true, false>), SMEM_BYTES)
+    CLB_SMEM_ATTR((k_pileup_general<false, true>), SMEM_BYTES) CLB_SMEM_ATTR((k_pileup_general<true, true>), SMEM_BYTES)
+    CLB_SMEM_ATTR((k_pileup_classify_deep<false, false>), SMEM_BYTES_DEEP) CLB_SMEM_ATTR((k_pileup_classify_deep<true, false>), SMEM_BYTES_DEEP)
+    CLB_SMEM_ATTR((k_pileup_classify_deep<false, true>), SMEM_BYTES_DEEP) CLB_SMEM_ATTR((k_pileup_classify_deep<true, true>), SMEM_BYTES_DEEP)
+    CLB_SMEM_ATTR((k_pileup_fast<false, false>), F_SMEM) CLB_SMEM_ATTR((k_pileup_fast<true, false>), F_SMEM)
+    CLB_SMEM_ATTR((k_pileup_fast<false, true>), F_SMEM) CLB_SMEM_ATTR((k_pileup_fast<true, true>), F_SMEM)
+#undef CLB_SMEM_ATTR
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_general<false, false>, NT, SMEM_BYTES);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc((void **)&ctx->d_first_tab, 65536 * 4 + WIN_TABLE_BYTES)) != cudaSuccess) { clb_destroy(ctx); return bail("cudaMalloc", e); }
     k_first_table<<<65536 / 256, 256, 0, ctx->s_compute>>>(ctx->d_first_tab, opt->max_low_mapq_fraction);
@@ -348,7 +393,7 @@ void clb_destroy(clb_ctx *ctx) {
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end, &ctx->cigar_ckpt,
                       &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_r,
-                      &ctx->win_q, &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
+                      &ctx->win_q, &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->win_g, &ctx->gen_list, &ctx->blk_tot, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
         release(*b);
     if (ctx->d_first_tab) cudaFree(ctx->d_first_tab);
     if (ctx->h_intervals) cudaFreeHost(ctx->h_intervals);
@@ -559,15 +604,16 @@ int clb_rerun_resident(clb_ctx *ctx, clb_contig_result *out, float *ms) {
     CU(cudaSetDevice(ctx->device));
     int rc;
     const uint32_t l0 = ctx->launches;
-    float t = 0, tp = 0;
-    if ((rc = run_all_resident(ctx, &t, &tp))) return rc;
+    float t = 0, tp = 0, tf = 0;
+    if ((rc = run_all_resident(ctx, &t, &tp, &tf))) return rc;
     if (ms) *ms = t;
     if (out) {
         rc = fetch_result(ctx, out);
         if (rc == 1) return fail(ctx, CLB_E_CUDA, "record buffer overflow on re-run");
         if (rc) return rc;
-        out->kernel_ms = t; out->pileup_ms = tp;
+        out->kernel_ms = t; out->pileup_ms = tp; out->fast_ms = tf;
         out->gpu_launches = ctx->launches - l0;
+        out->general_windows = ctx->h_misc[M_GEN_COUNT];
     }
     return CLB_OK;
 }

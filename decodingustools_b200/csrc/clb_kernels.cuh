@@ -88,6 +88,10 @@ struct KParams {
     uint2 *win_tab;                // per window: (first record, record count)
     uint32_t *err;
     uint32_t *deep_count, *deep_list;   // windows with more than 65535 candidate reads, left to k_pileup_classify_deep
+    // per window: x = reads per sub-batch of k_pileup_fast (0: general-path window), y = staged bytes of its first sub-batch
+    const uint2 *win_g;
+    uint32_t *gen_list, *gen_count, *gen_taken;   // queue of general-path windows (k_pileup_general takes tickets)
+    const uint32_t *max_span;           // upper bound of the reference span of any read of the contig
     // optional per-base debug output, indexed by position - region_start
     uint32_t *dbg_raw, *dbg_qc, *dbg_low;
     uint8_t *dbg_state;
@@ -377,6 +381,9 @@ __device__ __forceinline__ uint32_t first_low(uint32_t raw, double fraction) {
     return lo;
 }
 
+#ifndef CLB_F_STAGE
+#define CLB_F_STAGE 36864                 // quality bytes k_pileup_fast stages per sub-batch (clb_fast.cuh)
+#endif
 #ifndef CLB_PREFETCH_MAX
 #define CLB_PREFETCH_MAX (128u << 10)     // bytes of a window's qualities prefetched into L2 at window start
 #endif
@@ -746,6 +753,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         }
     }
     sLast[tid] = (uint8_t)((uint32_t)(stp >> (4 * (PPT - 1))) & 15u);
+    if (k_end > k_first && ebase + k_end == n_ent) sScan[3 * NWARPS + 1] = (uint32_t)(stp >> (4 * (k_end - 1))) & 15u;   // state of the window's last position
     // per-warp partial sums of the additive counters (plain stores, summed after the barrier: no 64-bit smem atomics)
     {
         uint32_t v[10];
@@ -805,7 +813,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
         if (tid == 0) {
             const uint32_t base = total ? atomicAdd(P.rec_cursor, total) : 0u;
             sScan[3 * NWARPS] = base;
-            P.win_tab[w] = make_uint2(base, total);
+            P.win_tab[w] = make_uint2(base, total | (sScan[3 * NWARPS + 1] << 20));   // count | last state << 20 (see pack_win_y)
             if (total && (unsigned long long)base + total > P.rec_cap) atomicOr(P.err, ERR_REC_OVERFLOW);
         }
         __syncthreads();
@@ -868,18 +876,34 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
 #undef CLB_STAMP
 }
 
+// General kernel: persistent CTAs take the windows queued by k_window_ranges / k_pileup_fast one ticket at a time.
+// The queue only grows between launches (all pushes of a batch of windows happen before this kernel starts on the
+// same stream), so a CTA that draws a ticket past the end gives it back and leaves: gen_taken == gen_count afterwards.
 template <bool BQ_HI, bool DBG>
-__global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_classify(const KParams P) {
-    pileup_classify_window<BQ_HI, false, DBG>(P, P.win_first + blockIdx.x);
+__global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_general(const KParams P) {
+    __shared__ uint32_t s_ticket;
+    const uint32_t n = *P.gen_count;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            uint32_t t = atomicAdd(P.gen_taken, 1u);
+            if (t >= n) { atomicSub(P.gen_taken, 1u); t = 0xffffffffu; }
+            s_ticket = t;
+        }
+        __syncthreads();
+        const uint32_t t = s_ticket;
+        if (t == 0xffffffffu) break;
+        pileup_classify_window<BQ_HI, false, DBG>(P, P.gen_list[t]);
+        __syncthreads();                                     // shared memory (and s_ticket) are reused by the next window
+    }
 }
 
 // Second pass over the (rare) windows k_pileup_classify queued because they hold more than 65535 candidate reads:
 // a fixed small grid walks the queue; with an empty queue the launch costs a few microseconds.
-template <bool BQ_HI>
+template <bool BQ_HI, bool DBG>
 __global__ void __launch_bounds__(NT, 1) k_pileup_classify_deep(const KParams P) {
     const uint32_t n = *P.deep_count;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        pileup_classify_window<BQ_HI, true, true>(P, P.deep_list[i]);
+        pileup_classify_window<BQ_HI, true, DBG>(P, P.deep_list[i]);
         __syncthreads();                                     // shared memory is reused by the next window
     }
 }
@@ -893,10 +917,13 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t
     return lo;
 }
 
-// candidate read range of every window: reads with pos < window end and pos + max_span > halo position
+// candidate read range of every window: reads with pos < window end and pos + max_span > halo position; and the
+// window's class: shard-first windows (they need the state of the base before the shard), windows of long-read contigs
+// and windows whose candidate count or CIGAR density cannot be an ordinary short-read pile go straight to the general queue.
 __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t region_start, uint32_t region_end,
                                 const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w,
-                                const uint64_t *qual_off, uint32_t stride, uint4 *win_r, ulonglong2 *win_q) {
+                                const uint64_t *qual_off, const uint32_t *cigar_off, uint32_t stride, uint4 *win_r, ulonglong2 *win_q,
+                                uint32_t force_general, uint2 *win_g, uint32_t *gen_list, uint32_t *gen_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_w) return;
     const uint32_t max_span = *max_span_ptr;
@@ -905,8 +932,32 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     const long long wend = min(wb + WN, (long long)region_end);
     const uint32_t r_lo = lower_bound_pos(pos, n_reads, wb - (long long)max_span + 1), r_hi = lower_bound_pos(pos, n_reads, wend);
     const uint32_t first_bin = stride ? (uint32_t)(wb + 1) / stride : 0u;
+    const uint64_t q_lo = qual_off[r_lo] & ~15ull, q_hi = qual_off[r_hi];
     win_r[w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
-    win_q[w] = make_ulonglong2(qual_off[r_lo] & ~15ull, qual_off[r_hi]);
+    win_q[w] = make_ulonglong2(q_lo, q_hi);
+    const uint32_t n_cand = r_hi - r_lo;
+    bool general = force_general != 0 || (w == 0 && region_start != 0) || n_cand > 16384u || q_hi - q_lo > 0xfffffff0ull;
+    if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
+    // Sub-batches of the fast kernel: G reads at a time (one per thread) whose qualities fit its stage.  Start from the
+    // mean read length of the window and verify every sub-batch; shrink a few times before giving up.
+    uint32_t G = NT, bytes0 = 0;
+    if (!general && n_cand) {
+        const uint64_t total = q_hi - q_lo;
+        if (total > (uint64_t)CLB_F_STAGE) G = min((uint32_t)NT, (uint32_t)(((uint64_t)(CLB_F_STAGE - 16) * n_cand) / total) & ~1u);
+        bool ok = false;
+        for (int tries = 0; tries < 4 && G >= 32u && !ok; tries++) {
+            ok = true;
+            for (uint32_t b = r_lo; b < r_hi; b += G) {
+                const uint64_t bytes = (qual_off[min(b + G, r_hi)] - (qual_off[b] & ~15ull) + 15ull) & ~15ull;
+                if (b == r_lo) bytes0 = (uint32_t)min(bytes, (uint64_t)0xffffffffu);
+                if (bytes > (uint64_t)CLB_F_STAGE) { ok = false; break; }
+            }
+            if (!ok) G -= min(G, 16u);
+        }
+        if (!ok) general = true;
+    }
+    win_g[w] = make_uint2(general ? 0u : G, general ? 0u : bytes0);
+    if (general) gen_list[atomicAdd(gen_count, 1u)] = w;
 }
 
 // pos + reference span of every read, and the maximum span (long-read mode / max_ref_span == 0)
@@ -1004,26 +1055,51 @@ __global__ void k_first_table(uint32_t *first_tab, double fraction) {
 // ---------------------------------------------------------------------------------------------
 struct IntervalOut { uint32_t start, end; uint8_t state, soft; uint16_t pad; };
 
-// single block: exclusive scan of per-window record counts
-__global__ void k_scan_windows(const uint2 *win_tab, uint32_t n_w, uint32_t *win_out, uint32_t *n_total) {
+// Records a window contributes to the sorted interval list: its count, minus the first record when that one is only
+// "window soft" (fast kernel: emitted unconditionally for the window's first position) and the previous window ended
+// in the same state.  win_tab[w].y = count | first state << 12 | window soft << 16 | last state << 20.
+__device__ __forceinline__ uint32_t win_drop_first(const uint2 *win_tab, uint32_t w) {
+    const uint32_t y = win_tab[w].y;
+    if (!((y >> 16) & 1u) || w == 0) return 0u;
+    return ((y >> 12) & 15u) == ((win_tab[w - 1].y >> 20) & 15u) ? 1u : 0u;
+}
+
+// step 1: every block scans 1024 windows locally and publishes its total
+__global__ void __launch_bounds__(1024) k_scan_windows_local(const uint2 *win_tab, uint32_t n_w, uint32_t *win_out, uint32_t *blk_tot) {
+    __shared__ uint32_t sW[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t i = blockIdx.x * 1024u + tid;
+    const uint32_t v = i < n_w ? (win_tab[i].y & 0xfffu) - win_drop_first(win_tab, i) : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, dd); if (lane >= dd) inc += t; }
+    if (lane == 31) sW[warp] = inc;
+    __syncthreads();
+    const uint32_t wt = sW[lane];
+    const uint32_t off = __reduce_add_sync(FULL, lane < warp ? wt : 0u);
+    if (i < n_w) win_out[i] = off + inc - v;
+    if (tid == 1023) blk_tot[blockIdx.x] = off + inc;
+}
+// step 2: one block turns the block totals into block offsets (in place) and the grand total
+__global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t *blk_tot, uint32_t n_blk, uint32_t *n_total) {
     __shared__ uint32_t sW[32];
     __shared__ uint32_t sCarry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sCarry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n_w; base += blockDim.x) {
+    for (uint32_t base = 0; base < n_blk; base += 1024u) {
         const uint32_t i = base + tid;
-        const uint32_t v = i < n_w ? win_tab[i].y : 0u;
+        const uint32_t v = i < n_blk ? blk_tot[i] : 0u;
         uint32_t inc = v;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, dd); if (lane >= dd) inc += t; }
         if (lane == 31) sW[warp] = inc;
         __syncthreads();
-        uint32_t off = sCarry;
-        for (int j = 0; j < warp; j++) off += sW[j];
-        if (i < n_w) win_out[i] = off + inc - v;
+        const uint32_t wt = sW[lane];
+        const uint32_t off = sCarry + __reduce_add_sync(FULL, lane < warp ? wt : 0u);
+        if (i < n_blk) blk_tot[i] = off + inc - v;
         __syncthreads();
-        if (tid == blockDim.x - 1) sCarry = off + inc;
+        if (tid == 1023) sCarry = off + inc;
         __syncthreads();
     }
     if (tid == 0) *n_total = sCarry;
@@ -1032,15 +1108,16 @@ __global__ void k_scan_windows(const uint2 *win_tab, uint32_t n_w, uint32_t *win
 // one warp per window: move its records to their sorted place (start/state/soft; end filled next)
 // (nothing to gather when the record buffer overflowed: the records past its capacity were never written and the
 // interval array is just as small; the host grows both and re-runs the contig)
-__global__ void k_gather_intervals(const unsigned long long *rec, const uint2 *win_tab, const uint32_t *win_out, uint32_t n_w,
-                                   IntervalOut *out, const uint32_t *err) {
+__global__ void k_gather_intervals(const unsigned long long *rec, const uint2 *win_tab, const uint32_t *win_out, const uint32_t *blk_off,
+                                   uint32_t n_w, IntervalOut *out, const uint32_t *err) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_w || (*err & ERR_REC_OVERFLOW)) return;
     const uint2 t = win_tab[w];
-    const uint32_t o = win_out[w];
-    for (uint32_t i = lane; i < t.y; i += 32) {
-        const unsigned long long r = rec[t.x + i];
+    const uint32_t skip = win_drop_first(win_tab, w);
+    const uint32_t o = blk_off[w >> 10] + win_out[w], cnt = (t.y & 0xfffu) - skip;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        const unsigned long long r = rec[t.x + skip + i];
         IntervalOut iv; iv.start = (uint32_t)r; iv.end = 0; iv.state = (uint8_t)(r >> 32); iv.soft = (uint8_t)((r >> 40) & 1u); iv.pad = 0;
         out[o + i] = iv;
     }

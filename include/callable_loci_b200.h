@@ -102,13 +102,13 @@ typedef struct clb_contig_result {
     uint32_t region_end;
     float    kernel_ms;              /* device time of the pileup/classify/segment kernels (CUDA events) */
     float    h2d_ms;                 /* device time of the host->device copies                          */
-    float    pileup_ms;              /* device time of the dominant kernel (k_pileup_classify) alone;
+    float    pileup_ms;              /* device time of the pileup kernels (k_pileup_fast + k_pileup_general) alone;
                                         only set by clb_rerun_resident                                  */
-    float    _pad0;
+    float    fast_ms;                /* of which k_pileup_fast (the dominant kernel); clb_rerun_resident only */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     uint32_t gpu_launches;           /* kernels launched for this contig */
-    uint32_t _pad;
+    uint32_t general_windows;        /* windows that took the general kernel (long CIGARs, deep piles, shard starts) */
 } clb_contig_result;
 
 typedef struct clb_ctx clb_ctx;
