@@ -136,6 +136,7 @@ KParams make_params(clb_ctx *c) {
     P.min_mapq = c->opt.min_mapping_quality; P.min_bq = c->opt.min_base_quality; P.max_low_mapq = c->opt.max_low_mapq;
     P.first_tab = c->d_first_tab;
     P.win_tables = c->d_first_tab + 65536;
+    P.first_tab8 = (const uint8_t *)(c->d_first_tab + 65536) + WIN_TABLE_BYTES;
     P.win_r = (const uint4 *)c->win_r.p; P.win_q = (const ulonglong2 *)c->win_q.p;
     P.stats = (unsigned long long *)c->stats_padded.p;
     P.bins = (unsigned long long *)c->counters.p + N_STATS;
@@ -379,8 +380,8 @@ clb_ctx *clb_create(int device, const clb_options *opt, char *err, size_t err_le
 #undef CLB_SMEM_ATTR
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->max_ctas_per_sm, k_pileup_general<false, false>, NT, SMEM_BYTES);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if ((e = cudaMalloc((void **)&ctx->d_first_tab, 65536 * 4 + WIN_TABLE_BYTES)) != cudaSuccess) { clb_destroy(ctx); return bail("cudaMalloc", e); }
-    k_first_table<<<65536 / 256, 256, 0, ctx->s_compute>>>(ctx->d_first_tab, opt->max_low_mapq_fraction);
+    if ((e = cudaMalloc((void **)&ctx->d_first_tab, 65536 * 4 + WIN_TABLE_BYTES + 256)) != cudaSuccess) { clb_destroy(ctx); return bail("cudaMalloc", e); }
+    k_first_table<<<65536 / 256, 256, 0, ctx->s_compute>>>(ctx->d_first_tab, (uint8_t *)(ctx->d_first_tab + 65536) + WIN_TABLE_BYTES, opt->max_low_mapq_fraction);
     k_window_tables<<<1, 256, 0, ctx->s_compute>>>(ctx->d_first_tab + 65536, opt->max_low_mapq_fraction);
     if ((e = cudaHostAlloc((void **)&ctx->h_misc, M_WORDS * 4, cudaHostAllocDefault)) != cudaSuccess) { clb_destroy(ctx); return bail("cudaHostAlloc", e); }
     if ((e = cudaStreamSynchronize(ctx->s_compute)) != cudaSuccess) { clb_destroy(ctx); return bail("first-table kernel", e); }

@@ -24,34 +24,34 @@
 namespace clb {
 
 constexpr int F_CW = 520;                 // words per alignment-class array (2048 / 4 + 8; 520 % 32 == 8 staggers the banks)
-constexpr int F_STAGE = CLB_F_STAGE;      // staged quality bytes per sub-batch (k_window_ranges sizes the sub-batches to fit)
-constexpr int F_XCAP = 64;                // second-and-later M-segments per sub-batch (two lists: one being filled, one being streamed)
+constexpr int F_WSTAGE = CLB_F_WSTAGE;    // staged quality bytes per warp and sub-batch of <= 32 reads (k_window_ranges sizes the sub-batches)
+constexpr int F_XCAP = 128;               // second-and-later M-segments per window (streamed from global memory at the end)
 constexpr int F_MAXOPS = 64;              // longest CIGAR walked lane-serially
 constexpr int F_LOOKBACK = 254;           // depth proof: pos[i] - pos[i - 254] >= max span  =>  depth <= 254 everywhere
-constexpr int F_NFIRST = 256;             // low-MAPQ threshold table entries (raw depth <= 254)
+constexpr int F_NFIRST = 256;             // low-MAPQ threshold table entries, one byte each (raw depth <= 254)
 #ifndef CLB_F_MINB
 #define CLB_F_MINB 4
 #endif
 
-// shared memory: A | C (4 class arrays) | stage | X lists | byte masks | first table | control words | 2 mbarriers.
-// The scratch of phase C (scan, last states, warp stats) reuses the stage, which is idle by then.
+// shared memory: A | C (4 class arrays) | one stage per warp | X list | byte masks | first table (u8) | control words | one mbarrier per warp.
+// The scratch of phase C (scan, last states, warp stats) reuses the stages, which are idle by then.
 constexpr int F_OFF_A = 0;
 constexpr int F_OFF_C = F_OFF_A + WN * 4;
 constexpr int F_OFF_STAGE = F_OFF_C + 4 * F_CW * 4;
-constexpr int F_OFF_X = F_OFF_STAGE + F_STAGE;
-constexpr int F_OFF_MASK = F_OFF_X + 2 * F_XCAP * 8;
+constexpr int F_OFF_X = F_OFF_STAGE + NWARPS * F_WSTAGE;
+constexpr int F_OFF_MASK = F_OFF_X + F_XCAP * 8;
 constexpr int F_OFF_FIRST = F_OFF_MASK + 2 * 17 * 16;
-constexpr int F_OFF_CTL = F_OFF_FIRST + F_NFIRST * 4;
+constexpr int F_OFF_CTL = F_OFF_FIRST + F_NFIRST;
 constexpr int F_OFF_BAR = F_OFF_CTL + 16 * 4;
-constexpr size_t F_SMEM = F_OFF_BAR + 32;
-constexpr int F_OFF_SCAN = F_OFF_STAGE;                        // phase C scratch inside the stage
+constexpr size_t F_SMEM = F_OFF_BAR + NWARPS * 8;
+constexpr int F_OFF_SCAN = F_OFF_STAGE;                        // phase C scratch inside the stages
 constexpr int F_OFF_LAST = F_OFF_SCAN + 64 * 4;
 constexpr int F_OFF_WSTATS = F_OFF_LAST + NT;
-static_assert(F_OFF_STAGE % 16 == 0, "bulk copies need a 16-byte aligned destination");
+static_assert(F_OFF_STAGE % 16 == 0 && F_WSTAGE % 16 == 0, "bulk copies need 16-byte aligned destinations");
 static_assert(F_OFF_WSTATS % 8 == 0 && F_OFF_BAR % 8 == 0 && F_OFF_X % 8 == 0 && F_OFF_MASK % 16 == 0 && F_OFF_FIRST % 16 == 0, "alignment");
-static_assert(F_STAGE % 16 == 0 && F_OFF_WSTATS + NWARPS * N_STATS * 8 <= F_OFF_X, "stage size");
+static_assert(F_OFF_WSTATS + NWARPS * N_STATS * 8 <= F_OFF_X, "phase C scratch fits the stages");
 static_assert(CLB_F_MINB * (F_SMEM + 1024) <= 228 * 1024, "shared memory per SM");
-enum { FC_BAIL = 0, FC_XCNT = 1 /* 3 counters */, FC_SB = 4 /* 2 stage bases */ };
+enum { FC_BAIL = 0, FC_XCNT = 1 };
 
 // window table word y: record count | first state << 12 | window-soft first record << 16 | last state << 20
 __device__ __forceinline__ uint32_t pack_win_y(uint32_t count, uint32_t first_state, uint32_t wsoft, uint32_t last_state) {
@@ -64,6 +64,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
@@ -136,6 +139,30 @@ __device__ __forceinline__ void stream_segment(uint32_t stage_s, uint32_t sC_s, 
     }
 }
 
+// Same from global memory (the few second-and-later M-segments of a window: their qualities are in L2, one 16-byte
+// load per chunk; src0 = 16-byte aligned address of the window's first quality byte, qs relative to it).
+template <bool BQ_HI>
+__device__ __forceinline__ void stream_segment_global(const uint8_t *src0, uint32_t sC_s, uint32_t qs, uint32_t len, uint32_t rrel,
+                                                      const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc,
+                                                      uint32_t c_first, uint32_t c_step) {
+    const uint32_t head = qs & 15u;
+    const uint32_t nc = (head + len + 15u) >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(src0 + (qs & ~15u));
+    const int e0 = (int)rrel - (int)head;
+    const uint32_t dst0 = sC_s + ((uint32_t)e0 & 3u) * (uint32_t)(F_CW * 4) + (uint32_t)(((e0 >> 2) + 4) * 4);
+#pragma unroll 1
+    for (uint32_t c = c_first; c < nc; c += c_step) {              // the caller spreads the chunks of a segment over c_step threads
+        const uint32_t dst = dst0 + 16u * c;
+        const uint4 v = ldg_stream(src + c);
+        const uint32_t lo = c == 0 ? head : 0u, hi = min(16u, head + len - 16u * c);
+        const uint4 ml = sMaskLo[lo], mh = sMaskHi[hi];
+        const uint32_t l0 = bytes_ge<BQ_HI>(v.x, t_low) & ~(ml.x | mh.x), l1 = bytes_ge<BQ_HI>(v.y, t_low) & ~(ml.y | mh.y);
+        const uint32_t l2 = bytes_ge<BQ_HI>(v.z, t_low) & ~(ml.z | mh.z), l3 = bytes_ge<BQ_HI>(v.w, t_low) & ~(ml.w | mh.w);
+        acc = __dp4a(v.x, l0, __dp4a(v.y, l1, __dp4a(v.z, l2, __dp4a(v.w, l3, acc))));
+        red_shared(dst, l0 >> 7); red_shared(dst + 4, l1 >> 7); red_shared(dst + 8, l2 >> 7); red_shared(dst + 12, l3 >> 7);
+    }
+}
+
 // What a thread knows about its read of the next sub-batch: loaded one sub-batch ahead so that the DRAM round trips
 // overlap the streaming of the current one.
 struct FMeta {
@@ -152,7 +179,7 @@ template <bool BQ_HI, bool DBG>
 __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t w = P.win_first + blockIdx.x;
-    const uint2 wg = P.win_g[w];                                           // reads per sub-batch (0: general-path window), bytes of the first one
+    const uint2 wg = P.win_g[w];                                           // x: reads per sub-batch (0: general-path window)
     const uint32_t G = wg.x;
     if (G == 0) return;
 
@@ -161,77 +188,83 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     uint2 *sX = reinterpret_cast<uint2 *>(smem_raw + F_OFF_X);
     const uint4 *sMaskLo = reinterpret_cast<const uint4 *>(smem_raw + F_OFF_MASK);
     const uint4 *sMaskHi = sMaskLo + 17;
-    uint32_t *sFirst = reinterpret_cast<uint32_t *>(smem_raw + F_OFF_FIRST);
+    const uint8_t *sFirst = smem_raw + F_OFF_FIRST;
     uint32_t *sScan = reinterpret_cast<uint32_t *>(smem_raw + F_OFF_SCAN);
     uint8_t *sLast = smem_raw + F_OFF_LAST;
     unsigned long long *sWStats = reinterpret_cast<unsigned long long *>(smem_raw + F_OFF_WSTATS);
     volatile uint32_t *sCtl = reinterpret_cast<volatile uint32_t *>(smem_raw + F_OFF_CTL);
-    const uint32_t bar_full = smem_addr(smem_raw + F_OFF_BAR), bar_free = bar_full + 8;
-    const uint32_t sA_s = smem_addr(sA), sC_s = smem_addr(sC), stage_s = smem_addr(smem_raw + F_OFF_STAGE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sA_s = smem_addr(sA), sC_s = smem_addr(sC);
+    const uint32_t stage_s = smem_addr(smem_raw + F_OFF_STAGE) + (uint32_t)warp * F_WSTAGE;   // this warp's stage
+    const uint32_t bar = smem_addr(smem_raw + F_OFF_BAR) + 8u * (uint32_t)warp;                // and its mbarrier
+    const uint32_t xcnt_s = smem_addr(const_cast<uint32_t *>(&sCtl[FC_XCNT]));
 
     const long long wb0 = (long long)P.region_start + (long long)w * WREAL;              // position of entry 0
     const uint32_t n_ent = (uint32_t)min((long long)WREAL, (long long)P.region_end - wb0);   // entries in use, 1 .. WREAL
     const uint4 wr = P.win_r[w];
     const ulonglong2 wq = P.win_q[w];
     const uint32_t r_lo = wr.x, r_hi = wr.y;
+    const uint32_t n_sub = (r_hi - r_lo + G - 1u) / G;                     // sub-batches of G <= 32 reads; warp v takes v, v + 8, ...
     const uint32_t ebase = tid * PPT;
 
-    // loads whose latency the setup hides: the first sub-batch's read columns and the REF_N bits of phase C
+    // loads whose latency the setup hides: this warp's first sub-batch and the REF_N bits of phase C
     FMeta M;
-    const bool worker = (uint32_t)tid < G;
-    if (r_hi > r_lo) fmeta_load(P, M, min(r_lo + (uint32_t)tid, r_hi - 1u));
+    uint32_t j = (uint32_t)warp;
+    if (j < n_sub) fmeta_load(P, M, min(r_lo + j * G + (uint32_t)lane, r_hi - 1u));
     uint32_t nm0, nm1;
     {
         const long long p0 = wb0 + (long long)ebase;
         nm0 = P.nmask[(uint32_t)(p0 >> 5)]; nm1 = P.nmask[(uint32_t)(p0 >> 5) + 1];
     }
     const uint32_t max_span = r_hi > r_lo ? *P.max_span : 0u;
+    if (tid == 0 && r_hi > r_lo) l2_prefetch(P.qual, wq.x, wq.y, CLB_PREFETCH_MAX);   // the window's qualities start moving into L2
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
         for (int i = tid; i < (F_OFF_STAGE / 16); i += NT) z[i] = make_uint4(0, 0, 0, 0);
         const uint4 *msrc = reinterpret_cast<const uint4 *>(P.win_tables);               // byte masks (first 2 x 17 x 16 bytes)
         uint4 *mdst = reinterpret_cast<uint4 *>(smem_raw + F_OFF_MASK);
         if (tid < 34) mdst[tid] = msrc[tid];
-        const uint4 *fsrc = reinterpret_cast<const uint4 *>(P.first_tab);
-        uint4 *fdst = reinterpret_cast<uint4 *>(sFirst);
-        if (tid >= 64 && tid < 64 + F_NFIRST / 4) fdst[tid - 64] = fsrc[tid - 64];
-        if (tid < 8) sCtl[tid] = 0;
-        if (tid == 0) { mbar_init(bar_full, NT); mbar_init(bar_free, NT); }
+        const uint4 *fsrc = reinterpret_cast<const uint4 *>(P.first_tab8);
+        uint4 *fdst = reinterpret_cast<uint4 *>(smem_raw + F_OFF_FIRST);
+        if (tid >= 64 && tid < 64 + F_NFIRST / 16) fdst[tid - 64] = fsrc[tid - 64];
+        if (tid < 4) sCtl[tid] = 0;
+        if (lane == 0) mbar_init(bar, 1);
     }
     __syncthreads();
-    if (tid == 0 && r_hi > r_lo) {
-        // the first sub-batch goes straight to shared memory; the rest of the window's qualities start moving into L2
-        if (wg.y) { mbar_expect_tx(bar_full, wg.y); bulk_g2s(stage_s, P.qual + wq.x, wg.y, bar_full); }
-        l2_prefetch(P.qual, wq.x + wg.y, wq.y, CLB_PREFETCH_MAX);
-    }
-    if (r_hi > r_lo) M.op0 = M.c1 > M.c0 ? P.cigar[M.c0] : 0xfu;
+    if (j < n_sub) M.op0 = M.c1 > M.c0 ? P.cigar[M.c0] : 0xfu;
 
     const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
     const uint32_t min_mapq = P.min_mapq, max_low_mapq = P.max_low_mapq;
     uint32_t acc128 = 0;                                                   // 128 x sum of passing qualities of the current sub-batch
     unsigned long long acc_sum = 0, acc_mapq = 0;
-    uint32_t sub = 0;
+    uint32_t parity = 0;
 
-    for (uint32_t rb = r_lo; rb < r_hi; sub++) {
-        const uint32_t re = min(r_hi, rb + G);
-        const bool has_next = re < r_hi;
-        const uint32_t xcnt_s = smem_addr(const_cast<uint32_t *>(&sCtl[FC_XCNT + sub % 3u]));
-        uint2 *xl = sX + (sub & 1u) * F_XCAP;
-        if (tid == 0) sCtl[FC_XCNT + (sub + 1u) % 3u] = 0;                 // last used two sub-batches ago; next used after this barrier
+    // Every warp runs its own pipeline: bulk copy of its sub-batch's qualities -> CIGAR walk while the copy is in
+    // flight -> next sub-batch's columns requested -> wait for the copy -> stream.  Only __syncwarp inside.
+    for (; j < n_sub; j += NWARPS) {
+        const uint32_t rb = r_lo + j * G, n = min(G, r_hi - rb);
+        __syncwarp();                                                      // every lane is done with the stage
+        const uint64_t q_first = __shfl_sync(FULL, M.q0, 0), q_last = __shfl_sync(FULL, M.q1, (int)n - 1);
+        const uint64_t sb = q_first & ~15ull;                              // stage byte 0 <-> this byte of the quality column
+        const uint64_t bytes64 = (q_last - sb + 15ull) & ~15ull;
+        const uint32_t bytes = bytes64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)bytes64;
+        const bool fits = bytes <= (uint32_t)F_WSTAGE;                     // k_window_ranges sized the sub-batches: always true
+        if (!fits) sCtl[FC_BAIL] = 1;
+        if (lane == 0 && fits && bytes) { mbar_arrive_expect_tx(bar, bytes); bulk_g2s(stage_s, P.qual + sb, bytes, bar); }
 
-        // ---------------------------------------------------------------- phase A: one read per thread
-        bool has0 = false; uint32_t s_qs = 0, s_len = 0, s_rr = 0;         // s_qs: relative to the window's first quality byte for now
+        // ---------------------------------------------------------------- phase A: one read per lane
+        bool has0 = false; uint32_t s_qs = 0, s_len = 0, s_rr = 0;
         {
-            const bool valid = worker && rb + (uint32_t)tid < re;
+            const bool valid = (uint32_t)lane < n;
             const bool live = valid && !(M.fl & 4u) && M.c1 > M.c0;
             uint32_t nops = live ? M.c1 - M.c0 : 0u;
-            const uint32_t ic = rb + (uint32_t)tid;
+            const uint32_t ic = rb + (uint32_t)lane;
             const bool deep = valid && ic >= (uint32_t)F_LOOKBACK && (long long)M.pback + (long long)max_span > (long long)M.ps;
             if (deep || nops > (uint32_t)F_MAXOPS) { sCtl[FC_BAIL] = 1; nops = 0; }
             const uint64_t ql = M.q1 - M.q0;
             const uint32_t lq = ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql;
-            const uint32_t qs_base = (uint32_t)(M.q0 - wq.x);
+            const uint32_t qs_base = (uint32_t)(M.q0 - sb);                // offset of the read's first quality inside the stage
+            const uint32_t qx_base = (uint32_t)(M.q0 - wq.x);              // ... and relative to the window's first quality byte
             const int rel = (int)((long long)M.ps - wb0);
             const uint32_t mq = M.mq, c0 = M.c0;
             const bool pass = mq >= min_mapq;
@@ -245,11 +278,11 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
                     const int s = max(rp, 0);
                     const int e = (int)min((long long)rp + (long long)l, (long long)n_ent);
                     if (e > s) {
-                        const uint32_t qs = qs_base + qp + (uint32_t)(s - rp);
-                        if (!has0) { has0 = true; s_qs = qs; s_len = (uint32_t)(e - s); s_rr = (uint32_t)s; }
+                        const uint32_t qo = qp + (uint32_t)(s - rp);
+                        if (!has0) { has0 = true; s_qs = qs_base + qo; s_len = (uint32_t)(e - s); s_rr = (uint32_t)s; }
                         else {
                             const uint32_t idx = atom_shared_add(xcnt_s, 1u);
-                            if (idx < (uint32_t)F_XCAP) xl[idx] = make_uint2(qs, (uint32_t)s | ((uint32_t)(e - s) << 11));
+                            if (idx < (uint32_t)F_XCAP) sX[idx] = make_uint2(qx_base + qo, (uint32_t)s | ((uint32_t)(e - s) << 11));
                             else sCtl[FC_BAIL] = 1;
                         }
                     }
@@ -267,43 +300,34 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
                 }
             }
         }
-        // the next sub-batch's columns: in flight while this one is streamed
-        uint64_t q_end_next = 0;
-        if (has_next) {
-            fmeta_load(P, M, min(re + (uint32_t)tid, r_hi - 1u));
-            if (tid == 0) q_end_next = P.qual_off[min(r_hi, re + G)];
-        }
-        mbar_arrive(bar_full);
-        mbar_wait(bar_full, sub & 1u);                                     // every thread's phase A + the staged qualities
-        if (sCtl[FC_BAIL]) {
-            // not an ordinary window after all: hand it to the general kernel (nothing global was written yet)
-            if (tid == 0) P.gen_list[atomicAdd(P.gen_count, 1u)] = w;
-            return;
-        }
-        const uint32_t sb_rel = sCtl[FC_SB + (sub & 1u)];                  // stage byte 0, relative to the window's first quality byte
+        // this warp's next sub-batch: its columns are in flight while the current one is streamed
+        const bool has_next = j + NWARPS < n_sub;
+        if (has_next) fmeta_load(P, M, min(r_lo + (j + NWARPS) * G + (uint32_t)lane, r_hi - 1u));
+        if (fits && bytes) { mbar_wait(bar, parity); parity ^= 1u; }       // the staged qualities have landed
         if (has_next) M.op0 = M.c1 > M.c0 ? P.cigar[M.c0] : 0xfu;
         // ---------------------------------------------------------------- phase B: stream from shared memory
-        if (has0) stream_segment<BQ_HI>(stage_s, sC_s, s_qs - sb_rel, s_len, s_rr, sMaskLo, sMaskHi, t_low, acc128);
-        const uint32_t nx = min(sCtl[FC_XCNT + sub % 3u], (uint32_t)F_XCAP);
-        for (uint32_t x = tid; x < nx; x += NT) {
-            const uint2 d = xl[x];
-            stream_segment<BQ_HI>(stage_s, sC_s, d.x - sb_rel, d.y >> 11, d.y & 0x7ffu, sMaskLo, sMaskHi, t_low, acc128);
-        }
-        acc_sum += acc128 >> 7; acc128 = 0;                                // at most 2 x 2047 bases x 255 x 128 per sub-batch: no overflow
-        if (!has_next) break;
-        mbar_arrive(bar_free);                                             // this thread is done with the stage
-        if (tid == 0) {
-            // the stage is free once every thread has streamed its share: refill it for the next sub-batch
-            mbar_wait(bar_free, sub & 1u);
-            const uint64_t sb = M.q0 & ~15ull;                             // thread 0's next read is the sub-batch's first
-            const uint64_t bytes = (q_end_next - sb + 15ull) & ~15ull;
-            if (bytes > (uint64_t)F_STAGE) sCtl[FC_BAIL] = 1;              // k_window_ranges sized the sub-batches: cannot happen
-            else if (bytes) { mbar_expect_tx(bar_full, (uint32_t)bytes); bulk_g2s(stage_s, P.qual + sb, (uint32_t)bytes, bar_full); }
-            sCtl[FC_SB + ((sub + 1u) & 1u)] = (uint32_t)(sb - wq.x);
-        }
-        rb = re;
+        if (has0 && fits) stream_segment<BQ_HI>(stage_s, sC_s, s_qs, s_len, s_rr, sMaskLo, sMaskHi, t_low, acc128);
+        acc_sum += acc128 >> 7; acc128 = 0;                                // at most 2047 bases x 255 x 128 per sub-batch: no overflow
     }
-    __syncthreads();                                                       // counters final; the stage becomes phase C scratch
+    __syncthreads();                                                       // every warp's pushes / counters
+    if (sCtl[FC_BAIL]) {
+        // not an ordinary window after all: hand it to the general kernel (nothing global was written yet)
+        if (tid == 0) P.gen_list[atomicAdd(P.gen_count, 1u)] = w;
+        return;
+    }
+    {
+        // second-and-later M-segments of the window's reads (indels): few, pooled for the whole CTA, streamed from L2
+        const uint32_t nx = sCtl[FC_XCNT];
+        if (nx) {
+            for (uint32_t x = (uint32_t)tid >> 4; x < nx; x += NT / 16) {  // 16 threads per segment, one chunk each: one L2 round trip
+                const uint2 d = sX[x];
+                stream_segment_global<BQ_HI>(P.qual + wq.x, sC_s, d.x, d.y >> 11, d.y & 0x7ffu, sMaskLo, sMaskHi, t_low, acc128,
+                                             (uint32_t)tid & 15u, 16u);
+            }
+            acc_sum += acc128 >> 7;
+            __syncthreads();
+        }
+    }
 
     // ------------------------------------------------------------------ phase C: scan, classify, segment
     static_assert(PPT == 8, "phase C of the fast kernel is written for 8 entries per thread");
@@ -350,7 +374,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     for (int k = 0; k < PPT; k++) {
         const uint32_t raw = a[k] & 0xffffu, low = a[k] >> 16;
         const uint32_t qc = qcv[k];
-        const uint32_t fst = sFirst[raw];                                   // raw <= 254 (depth proof)
+        const uint32_t fst = sFirst[raw];                                   // one byte per depth: raw <= 254 (depth proof)
         const bool is_low = raw >= min_dflm && low >= fst;
         uint32_t s = qc > max_depth ? ST_EXCESSIVE : ST_CALLABLE;
         s = qc < min_depth ? ST_LOW_COVERAGE : s;

@@ -72,6 +72,7 @@ struct KParams {
     uint32_t min_depth, max_depth, min_depth_for_low_mapq;
     uint32_t min_mapq, min_bq, max_low_mapq;
     const uint32_t *first_tab;     // [65536] smallest low count with low/raw > fraction (f64, exact)
+    const uint8_t *first_tab8;     // [256] the same for raw depths below 256, one byte each (k_pileup_fast)
     const uint32_t *win_tables;    // WIN_TABLE_BYTES: the per-window shared-memory tables, ready to copy (k_window_tables)
     double max_low_mapq_fraction;  // for depths past the table (deep windows)
     // windows
@@ -88,7 +89,7 @@ struct KParams {
     uint2 *win_tab;                // per window: (first record, record count)
     uint32_t *err;
     uint32_t *deep_count, *deep_list;   // windows with more than 65535 candidate reads, left to k_pileup_classify_deep
-    // per window: x = reads per sub-batch of k_pileup_fast (0: general-path window), y = staged bytes of its first sub-batch
+    // per window: x = reads per warp sub-batch of k_pileup_fast (0: general-path window)
     const uint2 *win_g;
     uint32_t *gen_list, *gen_count, *gen_taken;   // queue of general-path windows (k_pileup_general takes tickets)
     const uint32_t *max_span;           // upper bound of the reference span of any read of the contig
@@ -381,8 +382,8 @@ __device__ __forceinline__ uint32_t first_low(uint32_t raw, double fraction) {
     return lo;
 }
 
-#ifndef CLB_F_STAGE
-#define CLB_F_STAGE 36864                 // quality bytes k_pileup_fast stages per sub-batch (clb_fast.cuh)
+#ifndef CLB_F_WSTAGE
+#define CLB_F_WSTAGE 4848                 // quality bytes one warp of k_pileup_fast stages per sub-batch of <= 32 reads (clb_fast.cuh)
 #endif
 #ifndef CLB_PREFETCH_MAX
 #define CLB_PREFETCH_MAX (128u << 10)     // bytes of a window's qualities prefetched into L2 at window start
@@ -938,21 +939,20 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     const uint32_t n_cand = r_hi - r_lo;
     bool general = force_general != 0 || (w == 0 && region_start != 0) || n_cand > 16384u || q_hi - q_lo > 0xfffffff0ull;
     if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
-    // Sub-batches of the fast kernel: G reads at a time (one per thread) whose qualities fit its stage.  Start from the
-    // mean read length of the window and verify every sub-batch; shrink a few times before giving up.
-    uint32_t G = NT, bytes0 = 0;
+    // Sub-batches of the fast kernel: G <= 32 reads at a time (one per lane) whose qualities fit a warp's stage.  Start
+    // from the mean read length of the window and verify every sub-batch; shrink a few times before giving up.
+    uint32_t G = 32, bytes0 = 0;
     if (!general && n_cand) {
         const uint64_t total = q_hi - q_lo;
-        if (total > (uint64_t)CLB_F_STAGE) G = min((uint32_t)NT, (uint32_t)(((uint64_t)(CLB_F_STAGE - 16) * n_cand) / total) & ~1u);
+        if (total * 32u > (uint64_t)(CLB_F_WSTAGE - 16) * n_cand) G = (uint32_t)(((uint64_t)(CLB_F_WSTAGE - 16) * n_cand) / total);
         bool ok = false;
-        for (int tries = 0; tries < 4 && G >= 32u && !ok; tries++) {
+        for (int tries = 0; tries < 4 && G >= 4u && !ok; tries++) {
             ok = true;
             for (uint32_t b = r_lo; b < r_hi; b += G) {
                 const uint64_t bytes = (qual_off[min(b + G, r_hi)] - (qual_off[b] & ~15ull) + 15ull) & ~15ull;
-                if (b == r_lo) bytes0 = (uint32_t)min(bytes, (uint64_t)0xffffffffu);
-                if (bytes > (uint64_t)CLB_F_STAGE) { ok = false; break; }
+                if (bytes > (uint64_t)CLB_F_WSTAGE) { ok = false; break; }
             }
-            if (!ok) G -= min(G, 16u);
+            if (!ok) G -= max(1u, G / 8u);
         }
         if (!ok) general = true;
     }
@@ -1044,10 +1044,12 @@ __global__ void k_window_tables(uint32_t *out, double fraction) {
     for (uint32_t i = t; i < (uint32_t)NRCP; i += blockDim.x) out[2 * 17 * 4 + NFIRST + i] = i > 1 ? 0xffffffffu / i + 1u : 0u;
 }
 
-__global__ void k_first_table(uint32_t *first_tab, double fraction) {
+__global__ void k_first_table(uint32_t *first_tab, uint8_t *first_tab8, double fraction) {
     const uint32_t raw = blockIdx.x * blockDim.x + threadIdx.x;
     if (raw >= 65536u) return;
-    first_tab[raw] = first_low(raw, fraction);
+    const uint32_t f = first_low(raw, fraction);
+    first_tab[raw] = f;
+    if (raw < 256u) first_tab8[raw] = (uint8_t)min(f, 255u);       // f <= raw + 1; depth 0 is NO_COVERAGE whatever the table says
 }
 
 // ---------------------------------------------------------------------------------------------
