@@ -56,8 +56,8 @@ struct clb_ctx {
 
     DevBuf pos, flag, mapq, cigar_off, cigar, qual_off, qual, read_end, cigar_ckpt;
     DevBuf nmask, ref_ascii;
-    DevBuf stats_padded, counters, rec, win_tab, win_r, win_q, win_out, deep_list, intervals, misc;
-    DevBuf win_g, gen_list, blk_tot;
+    DevBuf stats_padded, counters, rec, win_tab, win_rec, win_out, deep_list, intervals, misc;
+    DevBuf gen_list, blk_tot;
     DevBuf dbg_raw, dbg_qc, dbg_low, dbg_state, timing;
     uint32_t rec_cap = 0;
     bool dbg = false;
@@ -137,7 +137,7 @@ KParams make_params(clb_ctx *c) {
     P.first_tab = c->d_first_tab;
     P.win_tables = c->d_first_tab + 65536;
     P.first_tab8 = (const uint8_t *)(c->d_first_tab + 65536) + WIN_TABLE_BYTES;
-    P.win_r = (const uint4 *)c->win_r.p; P.win_q = (const ulonglong2 *)c->win_q.p;
+    P.win_rec = (const uint4 *)c->win_rec.p;
     P.stats = (unsigned long long *)c->stats_padded.p;
     P.bins = (unsigned long long *)c->counters.p + N_STATS;
     P.n_bins = c->n_bins; P.stride = c->stride;
@@ -146,7 +146,7 @@ KParams make_params(clb_ctx *c) {
     P.win_tab = (uint2 *)c->win_tab.p;
     P.err = (uint32_t *)c->misc.p + M_ERR;
     P.deep_count = (uint32_t *)c->misc.p + M_DEEP; P.deep_list = (uint32_t *)c->deep_list.p;
-    P.win_g = (const uint2 *)c->win_g.p; P.gen_list = (uint32_t *)c->gen_list.p;
+    P.gen_list = (uint32_t *)c->gen_list.p;
     P.gen_count = (uint32_t *)c->misc.p + M_GEN_COUNT; P.gen_taken = (uint32_t *)c->misc.p + M_GEN_TAKEN;
     P.max_span = (const uint32_t *)c->misc.p + M_MAXSPAN;
     P.max_low_mapq_fraction = c->opt.max_low_mapq_fraction;
@@ -167,8 +167,7 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     k_window_ranges<<<(n + 127) / 128, 128, 0, ctx->s_compute>>>(
         (const int32_t *)ctx->pos.p, (uint32_t)ctx->n_reads, ctx->region_start, ctx->region_end,
         (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p, (const uint32_t *)ctx->cigar_off.p, ctx->stride,
-        (uint4 *)ctx->win_r.p, (ulonglong2 *)ctx->win_q.p, all_general ? 1u : 0u, (uint2 *)ctx->win_g.p,
-        (uint32_t *)ctx->gen_list.p, (uint32_t *)ctx->misc.p + M_GEN_COUNT);
+        (uint4 *)ctx->win_rec.p, all_general ? 1u : 0u, (uint32_t *)ctx->gen_list.p, (uint32_t *)ctx->misc.p + M_GEN_COUNT);
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
@@ -242,12 +241,10 @@ int alloc_outputs(clb_ctx *ctx) {
     int rc;
     const size_t nw = std::max<size_t>(ctx->n_windows, 1);
     if ((rc = ensure(ctx, ctx->win_tab, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
-    if ((rc = ensure(ctx, ctx->win_r, nw * sizeof(uint4), false, ctx->s_compute))) return rc;
-    if ((rc = ensure(ctx, ctx->win_q, nw * sizeof(ulonglong2), false, ctx->s_compute))) return rc;
+    if ((rc = ensure(ctx, ctx->win_rec, nw * 3 * sizeof(uint4), false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->win_out, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->deep_list, nw * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->gen_list, nw * 4, false, ctx->s_compute))) return rc;
-    if ((rc = ensure(ctx, ctx->win_g, nw * sizeof(uint2), false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->blk_tot, ((nw + 1023) / 1024 + 1) * 4, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->rec, (size_t)ctx->rec_cap * 8, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->intervals, (size_t)ctx->rec_cap * sizeof(IntervalOut), false, ctx->s_compute))) return rc;
@@ -393,8 +390,8 @@ void clb_destroy(clb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->pos, &ctx->flag, &ctx->mapq, &ctx->cigar_off, &ctx->cigar, &ctx->qual_off, &ctx->qual, &ctx->read_end, &ctx->cigar_ckpt,
-                      &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_r,
-                      &ctx->win_q, &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->win_g, &ctx->gen_list, &ctx->blk_tot, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
+                      &ctx->nmask, &ctx->ref_ascii, &ctx->stats_padded, &ctx->counters, &ctx->rec, &ctx->win_tab, &ctx->win_rec,
+                      &ctx->win_out, &ctx->deep_list, &ctx->intervals, &ctx->misc, &ctx->gen_list, &ctx->blk_tot, &ctx->dbg_raw, &ctx->dbg_qc, &ctx->dbg_low, &ctx->dbg_state, &ctx->timing})
         release(*b);
     if (ctx->d_first_tab) cudaFree(ctx->d_first_tab);
     if (ctx->h_intervals) cudaFreeHost(ctx->h_intervals);

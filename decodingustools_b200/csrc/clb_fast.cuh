@@ -166,8 +166,14 @@ __device__ __forceinline__ void stream_segment_global(const uint8_t *src0, uint3
 // What a thread knows about its read of the next sub-batch: loaded one sub-batch ahead so that the DRAM round trips
 // overlap the streaming of the current one.
 struct FMeta {
-    int ps, pback; uint32_t fl, mq, c0, c1, op0; uint64_t q0, q1;
+    int ps, pback; uint32_t fl, mq, c0, c1, op0, op1, op2; uint64_t q0, q1;
 };
+// the first three CIGAR ops in one round trip (almost every short read has at most three)
+__device__ __forceinline__ void fmeta_ops(const KParams &P, FMeta &M) {
+    M.op0 = M.c1 > M.c0 ? P.cigar[M.c0] : 0xfu;
+    M.op1 = M.c1 > M.c0 + 1u ? P.cigar[M.c0 + 1u] : 0xfu;
+    M.op2 = M.c1 > M.c0 + 2u ? P.cigar[M.c0 + 2u] : 0xfu;
+}
 __device__ __forceinline__ void fmeta_load(const KParams &P, FMeta &M, uint32_t ic) {
     M.fl = P.flag[ic]; M.c0 = P.cigar_off[ic]; M.c1 = P.cigar_off[ic + 1];
     M.ps = P.pos[ic]; M.mq = P.mapq[ic];
@@ -179,9 +185,18 @@ template <bool BQ_HI, bool DBG>
 __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t w = P.win_first + blockIdx.x;
-    const uint2 wg = P.win_g[w];                                           // x: reads per sub-batch (0: general-path window)
+    // one table record per window, three independent 16-byte loads (no dependent round trip)
+    const uint4 wg = P.win_rec[3 * (size_t)w + 2];                         // x: reads per sub-batch (0: general-path window)
+    const uint4 wr = P.win_rec[3 * (size_t)w];
+    const ulonglong2 wq = *reinterpret_cast<const ulonglong2 *>(P.win_rec + 3 * (size_t)w + 1);
     const uint32_t G = wg.x;
     if (G == 0) return;
+#ifdef CLB_PHASE_TIMING      // developer builds only (scripts/phase_timing.py)
+#define CLB_FSTAMP(i) do { if (P.timing && threadIdx.x == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
+#else
+#define CLB_FSTAMP(i) do { } while (0)
+#endif
+    CLB_FSTAMP(0);
 
     uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw + F_OFF_A);
     uint32_t *sC = reinterpret_cast<uint32_t *>(smem_raw + F_OFF_C);
@@ -201,8 +216,6 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
 
     const long long wb0 = (long long)P.region_start + (long long)w * WREAL;              // position of entry 0
     const uint32_t n_ent = (uint32_t)min((long long)WREAL, (long long)P.region_end - wb0);   // entries in use, 1 .. WREAL
-    const uint4 wr = P.win_r[w];
-    const ulonglong2 wq = P.win_q[w];
     const uint32_t r_lo = wr.x, r_hi = wr.y;
     const uint32_t n_sub = (r_hi - r_lo + G - 1u) / G;                     // sub-batches of G <= 32 reads; warp v takes v, v + 8, ...
     const uint32_t ebase = tid * PPT;
@@ -231,7 +244,8 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
         if (lane == 0) mbar_init(bar, 1);
     }
     __syncthreads();
-    if (j < n_sub) M.op0 = M.c1 > M.c0 ? P.cigar[M.c0] : 0xfu;
+    CLB_FSTAMP(1);
+    if (j < n_sub) fmeta_ops(P, M);
 
     const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
     const uint32_t min_mapq = P.min_mapq, max_low_mapq = P.max_low_mapq;
@@ -271,7 +285,9 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             const uint32_t kmax = __reduce_max_sync(FULL, nops);
             int rp = rel; uint32_t qp = 0;
             for (uint32_t k = 0; k < kmax; k++) {
-                const uint32_t v = k < nops ? (k == 0 ? M.op0 : P.cigar[c0 + k]) : 0xfu;    // op 15, len 0: no effect
+                uint32_t v = k == 0 ? M.op0 : k == 1 ? M.op1 : M.op2;
+                if (k >= 3u && k < nops) v = P.cigar[c0 + k];
+                if (k >= nops) v = 0xfu;                                                   // op 15, len 0: no effect (skipped reads, shorter CIGARs)
                 const uint32_t op = v & 15u, len = v >> 4;
                 if (((0x181u >> op) & 1u) && pass && qp < lq && rp < (int)n_ent) {          // M, =, X with qualities, not right of the window
                     const uint32_t l = min(len, lq - qp);
@@ -301,12 +317,15 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             }
         }
         // this warp's next sub-batch: its columns are in flight while the current one is streamed
+        if (j == 0) CLB_FSTAMP(2);
         const bool has_next = j + NWARPS < n_sub;
         if (has_next) fmeta_load(P, M, min(r_lo + (j + NWARPS) * G + (uint32_t)lane, r_hi - 1u));
         if (fits && bytes) { mbar_wait(bar, parity); parity ^= 1u; }       // the staged qualities have landed
-        if (has_next) M.op0 = M.c1 > M.c0 ? P.cigar[M.c0] : 0xfu;
+        if (j == 0) CLB_FSTAMP(3);
+        if (has_next) fmeta_ops(P, M);
         // ---------------------------------------------------------------- phase B: stream from shared memory
         if (has0 && fits) stream_segment<BQ_HI>(stage_s, sC_s, s_qs, s_len, s_rr, sMaskLo, sMaskHi, t_low, acc128);
+        if (j == 0) CLB_FSTAMP(4);
         acc_sum += acc128 >> 7; acc128 = 0;                                // at most 2047 bases x 255 x 128 per sub-batch: no overflow
     }
     __syncthreads();                                                       // every warp's pushes / counters
@@ -329,6 +348,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
         }
     }
 
+    CLB_FSTAMP(5);
     // ------------------------------------------------------------------ phase C: scan, classify, segment
     static_assert(PPT == 8, "phase C of the fast kernel is written for 8 entries per thread");
     uint32_t a[PPT], qcv[PPT];
@@ -505,6 +525,11 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             }
         }
     }
+    CLB_FSTAMP(6);
+#ifdef CLB_PHASE_TIMING
+    if (P.timing && tid == 0) P.timing[(size_t)w * 8 + 7] = (long long)(r_hi - r_lo);
+#endif
+#undef CLB_FSTAMP
 }
 
 }  // namespace clb

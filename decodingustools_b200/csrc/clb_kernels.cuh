@@ -76,8 +76,10 @@ struct KParams {
     const uint32_t *win_tables;    // WIN_TABLE_BYTES: the per-window shared-memory tables, ready to copy (k_window_tables)
     double max_low_mapq_fraction;  // for depths past the table (deep windows)
     // windows
-    const uint4 *win_r;            // per window: candidate reads [x, y), first histogram bin z, window entry w where the next bin starts
-    const ulonglong2 *win_q;       // per window: quality bytes [x (16-byte aligned), y) of the candidate reads
+    // per window, three 16-byte words (k_window_ranges): [0] candidate reads [x, y), first histogram bin z, window entry w where the
+    // next bin starts; [1] quality bytes [lo (16-byte aligned), hi) of the candidate reads as two u64; [2] x = reads per warp
+    // sub-batch of k_pileup_fast (0: general-path window)
+    const uint4 *win_rec;
     uint32_t win_first;
     // outputs
     unsigned long long *stats;     // [N_STATS * STAT_STRIDE]
@@ -89,8 +91,6 @@ struct KParams {
     uint2 *win_tab;                // per window: (first record, record count)
     uint32_t *err;
     uint32_t *deep_count, *deep_list;   // windows with more than 65535 candidate reads, left to k_pileup_classify_deep
-    // per window: x = reads per warp sub-batch of k_pileup_fast (0: general-path window)
-    const uint2 *win_g;
     uint32_t *gen_list, *gen_count, *gen_taken;   // queue of general-path windows (k_pileup_general takes tickets)
     const uint32_t *max_span;           // upper bound of the reference span of any read of the contig
     // optional per-base debug output, indexed by position - region_start
@@ -437,8 +437,8 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
     W.n_ent = n_ent;
-    const uint4 wr = P.win_r[w];
-    const ulonglong2 wq = P.win_q[w];
+    const uint4 wr = P.win_rec[3 * (size_t)w];
+    const ulonglong2 wq = *reinterpret_cast<const ulonglong2 *>(P.win_rec + 3 * (size_t)w + 1);
     const uint32_t r_lo = wr.x, r_hi = wr.y;
     const uint32_t n_batches = (r_hi - r_lo + 31u) >> 5;
     const uint32_t n_lq = (n_batches + BPA - 1) / BPA;     // packed arrays needed
@@ -923,8 +923,8 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t
 // and windows whose candidate count or CIGAR density cannot be an ordinary short-read pile go straight to the general queue.
 __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t region_start, uint32_t region_end,
                                 const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w,
-                                const uint64_t *qual_off, const uint32_t *cigar_off, uint32_t stride, uint4 *win_r, ulonglong2 *win_q,
-                                uint32_t force_general, uint2 *win_g, uint32_t *gen_list, uint32_t *gen_count) {
+                                const uint64_t *qual_off, const uint32_t *cigar_off, uint32_t stride, uint4 *win_rec,
+                                uint32_t force_general, uint32_t *gen_list, uint32_t *gen_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_w) return;
     const uint32_t max_span = *max_span_ptr;
@@ -934,14 +934,14 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     const uint32_t r_lo = lower_bound_pos(pos, n_reads, wb - (long long)max_span + 1), r_hi = lower_bound_pos(pos, n_reads, wend);
     const uint32_t first_bin = stride ? (uint32_t)(wb + 1) / stride : 0u;
     const uint64_t q_lo = qual_off[r_lo] & ~15ull, q_hi = qual_off[r_hi];
-    win_r[w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
-    win_q[w] = make_ulonglong2(q_lo, q_hi);
+    win_rec[3 * (size_t)w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
+    *reinterpret_cast<ulonglong2 *>(win_rec + 3 * (size_t)w + 1) = make_ulonglong2(q_lo, q_hi);
     const uint32_t n_cand = r_hi - r_lo;
     bool general = force_general != 0 || (w == 0 && region_start != 0) || n_cand > 16384u || q_hi - q_lo > 0xfffffff0ull;
     if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
     // Sub-batches of the fast kernel: G <= 32 reads at a time (one per lane) whose qualities fit a warp's stage.  Start
     // from the mean read length of the window and verify every sub-batch; shrink a few times before giving up.
-    uint32_t G = 32, bytes0 = 0;
+    uint32_t G = 32;
     if (!general && n_cand) {
         const uint64_t total = q_hi - q_lo;
         if (total * 32u > (uint64_t)(CLB_F_WSTAGE - 16) * n_cand) G = (uint32_t)(((uint64_t)(CLB_F_WSTAGE - 16) * n_cand) / total);
@@ -956,7 +956,7 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
         }
         if (!ok) general = true;
     }
-    win_g[w] = make_uint2(general ? 0u : G, general ? 0u : bytes0);
+    win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, 0u, 0u, 0u);
     if (general) gen_list[atomicAdd(gen_count, 1u)] = w;
 }
 

@@ -23,9 +23,11 @@ rc = L.clb_debug_timing(ctx._h, buf.ctypes.data_as(C.c_void_p), nmax, C.byref(n)
 assert rc == 0
 t = buf[: n.value]
 busy = t[t[:, 7] > (300 if mode == 'short' else 20)]          # windows with a normal read load
-names = ["setup", "phaseA(round0)", "phaseB+rest rounds", "C: scan+classify+stats", "C: boundaries+records", "C: bins"]
+names = (["setup (tables, zeroing, first columns)", "warp 0: first CIGAR walk", "warp 0: wait for its bulk copy", "warp 0: first stream",
+          "rest of the loop + barriers + extras", "phase C"] if not os.environ.get("CLB_FORCE_GENERAL") else
+         ["setup", "phaseA(round0)", "phaseB+rest rounds", "C: scan+classify+stats", "C: boundaries+records", "C: bins"])
 d = np.diff(busy[:, :7], axis=1).astype(np.float64)
 tot = d.sum(axis=1)
 print(f"windows {n.value}, busy {busy.shape[0]}, mean candidates {busy[:,7].mean():.0f}, mean cycles/window {tot.mean():.0f}")
 for i, nm in enumerate(names):
-    print(f"  {nm:28s} {d[:, i].mean():9.0f} cyc  {100 * d[:, i].mean() / tot.mean():5.1f}%")
+    print(f"  {nm:44s} {d[:, i].mean():9.0f} cyc  {100 * d[:, i].mean() / tot.mean():5.1f}%")
