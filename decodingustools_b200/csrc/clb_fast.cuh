@@ -132,9 +132,15 @@ __device__ __forceinline__ void stream_segment(uint32_t stage_s, uint32_t sC_s, 
     uint32_t dst = sC_s + ((uint32_t)e0 & 3u) * (uint32_t)(F_CW * 4) + (uint32_t)(((e0 >> 2) + 4) * 4);
     chunk_edge<BQ_HI>(src, dst, head, min(16u, head + len), sMaskLo, sMaskHi, t_low, acc);
     if (nc > 1) {
-#pragma unroll 1
-        for (uint32_t c = 2; c < nc; c++) { src += 16; dst += 16; chunk_plain<BQ_HI>(src, dst, t_low, acc); }
+        uint32_t n_int = nc - 2u;                                          // interior chunks: no masks, two per trip
         src += 16; dst += 16;
+#pragma unroll 1
+        for (; n_int >= 2u; n_int -= 2u) {
+            chunk_plain<BQ_HI>(src, dst, t_low, acc);
+            chunk_plain<BQ_HI>(src + 16, dst + 16, t_low, acc);
+            src += 32; dst += 32;
+        }
+        if (n_int) { chunk_plain<BQ_HI>(src, dst, t_low, acc); src += 16; dst += 16; }
         chunk_edge<BQ_HI>(src, dst, 0u, head + len - 16u * (nc - 1u), sMaskLo, sMaskHi, t_low, acc);
     }
 }
@@ -250,7 +256,8 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     const uint32_t t_low = (P.min_bq & 0x7fu) * 0x01010101u;
     const uint32_t min_mapq = P.min_mapq, max_low_mapq = P.max_low_mapq;
     uint32_t acc128 = 0;                                                   // 128 x sum of passing qualities of the current sub-batch
-    unsigned long long acc_sum = 0, acc_mapq = 0;
+    // sums of one window fit 32 bits: at most 2047 positions x 254 reads (depth proof) x 255
+    uint32_t acc_sum = 0, acc_mapq = 0;
     uint32_t parity = 0;
 
     // Every warp runs its own pipeline: bulk copy of its sub-batch's qualities -> CIGAR walk while the copy is in
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
                 if (((0x181u >> op) & 1u) && pass && qp < lq && rp < (int)n_ent) {          // M, =, X with qualities, not right of the window
                     const uint32_t l = min(len, lq - qp);
                     const int s = max(rp, 0);
-                    const int e = (int)min((long long)rp + (long long)l, (long long)n_ent);
+                    const int e = min(rp + (int)l, (int)n_ent);                            // rp < 2048, l < 2^28: no overflow
                     if (e > s) {
                         const uint32_t qo = qp + (uint32_t)(s - rp);
                         if (!has0) { has0 = true; s_qs = qs_base + qo; s_len = (uint32_t)(e - s); s_rr = (uint32_t)s; }
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
                     const uint32_t delta = 1u + (mq <= max_low_mapq ? 0x10000u : 0u);       // raw depth | low-MAPQ depth << 16
                     red_shared(sA_s + 4u * (uint32_t)s, delta);
                     red_shared(sA_s + 4u * (uint32_t)e, 0u - delta);                        // e <= n_ent <= WREAL < WN
-                    if (pass) acc_mapq += (unsigned long long)mq * (uint32_t)(e - s);
+                    if (pass) acc_mapq += mq * (uint32_t)(e - s);
                 }
             }
         }
@@ -428,12 +435,10 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
         uint32_t v[10];
 #pragma unroll
         for (int s = 0; s < 6; s++) v[s] = (cnt_pack >> (5 * s)) & 31u;
-        v[6] = covered; v[7] = sraw; v[8] = 0; v[9] = sqc;
+        v[6] = covered; v[7] = sraw; v[8] = acc_sum; v[9] = sqc;
 #pragma unroll
-        for (int i = 0; i < 10; i++) if (i != 8) v[i] = __reduce_add_sync(FULL, v[i]);
-        unsigned long long mqs = acc_mapq, bqs = acc_sum;
-#pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) { mqs += __shfl_xor_sync(FULL, mqs, dd); bqs += __shfl_xor_sync(FULL, bqs, dd); }
+        for (int i = 0; i < 10; i++) v[i] = __reduce_add_sync(FULL, v[i]);
+        const uint32_t mqs = __reduce_add_sync(FULL, acc_mapq), bqs = v[8];
         if (lane == 0) {
             unsigned long long *ws = sWStats + warp * N_STATS;
 #pragma unroll
