@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     // Every warp runs its own pipeline: bulk copy of its sub-batch's qualities -> CIGAR walk while the copy is in
     // flight -> next sub-batch's columns requested -> wait for the copy -> stream.  Only __syncwarp inside.
     for (; j < n_sub; j += NWARPS) {
+        if (sCtl[FC_BAIL]) break;                                          // some warp found the window is not an ordinary one
         const uint32_t rb = r_lo + j * G, n = min(G, r_hi - rb);
         __syncwarp();                                                      // every lane is done with the stage
         const uint64_t q_first = __shfl_sync(FULL, M.q0, 0), q_last = __shfl_sync(FULL, M.q1, (int)n - 1);

@@ -939,6 +939,9 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     const uint32_t n_cand = r_hi - r_lo;
     bool general = force_general != 0 || (w == 0 && region_start != 0) || n_cand > 16384u || q_hi - q_lo > 0xfffffff0ull;
     if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
+    // the fast kernel's depth proof (pos[i] - pos[i - 254] >= max_span for every candidate), sampled: a deep pile fails it
+    // at the first sample and goes to the general kernel without a wasted attempt
+    for (uint32_t i2 = r_lo + 254u; !general && i2 < r_hi; i2 += 254u) general = (long long)pos[i2 - 254u] + (long long)max_span > (long long)pos[i2];
     // Sub-batches of the fast kernel: G <= 32 reads at a time (one per lane) whose qualities fit a warp's stage.  Start
     // from the mean read length of the window and verify every sub-batch; shrink a few times before giving up.
     uint32_t G = 32;
