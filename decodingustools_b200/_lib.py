@@ -53,7 +53,7 @@ SYMBOLS = [
     "clb_abi_version", "clb_device_count", "clb_window_positions", "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream",
     "clb_begin_contig", "clb_reserve", "clb_push_reads", "clb_finish_contig", "clb_rerun_resident",
     "clb_counters_device", "clb_refresh_counters", "clb_allreduce_nccl", "clb_debug_per_base",
-    "clb_admit_reads", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
+    "clb_admit_reads", "clb_admit_reads_mt", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
     "clb_bed_writer_close", "clb_stitch_intervals", "clb_bin_geometry",
 ]
 
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.clb_allreduce_nccl.argtypes = [vp, vp]
     L.clb_debug_per_base.argtypes = [vp, vp, vp, vp, vp]
     L.clb_admit_reads.argtypes = [i32, u32, u64, vp, vp, vp, vp, vp]
+    L.clb_admit_reads_mt.argtypes = [i32, u32, u64, vp, vp, vp, vp, u32, u32, vp, C.POINTER(u64)]
     L.clb_compact_reads.argtypes = [C.POINTER(ReadBatch), vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(ReadBatch)]
     L.clb_bed_writer_open.restype = vp
     L.clb_bed_writer_open.argtypes = [C.c_char_p, u32]

@@ -177,14 +177,23 @@ class CallableLociContext:
 # ------------------------------------------------------------------------------------------------
 # Host half
 # ------------------------------------------------------------------------------------------------
-def admit_reads(reads: ReadColumns, maxcnt: int, tid: int = 0) -> np.ndarray:
-    """htslib's pileup admission (depth cap) as the reference configures it: mod.rs:55-60."""
+def admit_reads(reads: ReadColumns, maxcnt: int, tid: int = 0, threads: Optional[int] = None, max_ref_span: int = 0,
+                stats: Optional[dict] = None) -> np.ndarray:
+    """htslib's pileup admission (depth cap) as the reference configures it: mod.rs:55-60.
+    threads=None: the sequential recurrence (clb_admit_reads); otherwise the parallel form (clb_admit_reads_mt, 0 = all cores)."""
     keep = np.zeros(reads.n, dtype=np.uint8)
-    rc = _lib.lib().clb_admit_reads(int(tid), int(maxcnt), reads.n, _ptr(reads.pos), _ptr(reads.flag), _ptr(reads.cigar_off),
-                                    _ptr(reads.cigar), _ptr(keep))
+    if threads is None:
+        rc = _lib.lib().clb_admit_reads(int(tid), int(maxcnt), reads.n, _ptr(reads.pos), _ptr(reads.flag), _ptr(reads.cigar_off),
+                                        _ptr(reads.cigar), _ptr(keep))
+    else:
+        n_rep = C.c_uint64(0)
+        rc = _lib.lib().clb_admit_reads_mt(int(tid), int(maxcnt), reads.n, _ptr(reads.pos), _ptr(reads.flag), _ptr(reads.cigar_off),
+                                           _ptr(reads.cigar), int(max_ref_span), int(threads), _ptr(keep), C.byref(n_rep))
+        if stats is not None:
+            stats["replayed"] = int(n_rep.value)
     if rc != 0:
         raise ClbError(rc, "records are not coordinate sorted")
-    return keep.astype(bool)
+    return keep.view(np.bool_)
 
 
 def compact_reads(reads: ReadColumns, keep: np.ndarray) -> ReadColumns:

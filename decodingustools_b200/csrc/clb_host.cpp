@@ -6,49 +6,220 @@
 //   clb_stitch_intervals   region-shard stitching (multi-GPU)
 #include "../../include/callable_loci_b200.h"
 
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <functional>
-#include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 static const char *kStateName[6] = {"REF_N", "CALLABLE", "NO_COVERAGE", "LOW_COVERAGE", "EXCESSIVE_COVERAGE", "POOR_MAPPING_QUALITY"};
 
-extern "C" int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
-                               const uint32_t *cigar_off, const uint32_t *cigar, uint8_t *keep) {
-    // Closed form of the iterator mechanics: a record is dropped iff it is not the
-    // first record seen at its start position and the number of live nodes (admitted records whose
-    // end >= pos) has reached maxcnt.  The iterator starts at (tid 0, pos 0), so the very first record of
-    // tid 0 at pos 0 counts as "not first".  A zero-span record that is not first is never retained.
-    std::priority_queue<long long, std::vector<long long>, std::greater<long long>> live;   // min-heap of ends
-    long long last_pos = (tid == 0) ? 0 : -1;
-    bool any = false;
-    long long prev = -1;
-    for (uint64_t i = 0; i < n_reads; i++) {
+namespace {
+
+inline uint32_t ref_span(const uint32_t *cigar_off, const uint32_t *cigar, uint64_t i) {
+    uint32_t span = 0;
+    for (uint32_t c = cigar_off[i]; c < cigar_off[i + 1]; c++) {
+        const uint32_t op = cigar[c] & 15u;
+        if ((0x18du >> op) & 1u) span += cigar[c] >> 4;                       // M, D, N, =, X
+    }
+    return span;
+}
+
+// The iterator mechanics in closed form: a record is dropped iff it is not the first record seen
+// at its start position and the number of live nodes (admitted records whose end >= pos) has reached maxcnt.  The
+// iterator starts at (tid 0, pos 0), so the very first record of tid 0 at pos 0 counts as "not first".  A zero-span
+// record that is not first is never retained.  Live nodes are counted in a ring of end positions (O(1) per record,
+// O(contig length) in total) instead of a heap.
+struct LiveRing {
+    std::vector<uint32_t> cnt;      // cnt[e & mask] = live nodes ending at e, for e in [low, low + size)
+    uint64_t mask = 0;
+    long long low = 0;              // every end < low has expired
+    uint64_t live = 0;
+    std::vector<long long> far;     // ends beyond the ring (spans longer than expected): min-heap
+    void init(uint64_t max_span) {
+        uint64_t sz = 1024;
+        while (sz < max_span + 2) sz <<= 1;
+        cnt.assign(sz, 0); mask = sz - 1; low = 0; live = 0; far.clear();
+    }
+    void expire_below(long long p) {                       // drop nodes with end < p
+        if (p > low) {
+            if (live > far.size()) {
+                const long long stop = std::min<long long>(p, low + (long long)cnt.size());
+                for (long long e = low; e < stop; e++) { uint32_t &c = cnt[(uint64_t)e & mask]; live -= c; c = 0; }
+            }
+            low = p;
+        }
+        while (!far.empty() && far.front() < p) { std::pop_heap(far.begin(), far.end(), std::greater<long long>()); far.pop_back(); live--; }
+    }
+    void add(long long end) {
+        if (end < low + (long long)cnt.size()) cnt[(uint64_t)end & mask]++;
+        else { far.push_back(end); std::push_heap(far.begin(), far.end(), std::greater<long long>()); }
+        live++;
+    }
+};
+
+// sequential recurrence over records [lo, hi); state = ring + (any, last_pos)
+int admit_range(uint32_t maxcnt, uint64_t lo, uint64_t hi, const int32_t *pos, const uint16_t *flag, const uint32_t *cigar_off,
+                const uint32_t *cigar, uint8_t *keep, LiveRing &ring, bool &any, long long &last_pos, bool tid0, long long prev) {
+    for (uint64_t i = lo; i < hi; i++) {
         keep[i] = 0;
         if (flag[i] & 0x4) continue;
         const long long p = pos[i];
         if (p < prev) return CLB_E_INPUT;
         prev = p;
-        long long span = 0;
-        for (uint32_t c = cigar_off[i]; c < cigar_off[i + 1]; c++) {
-            const uint32_t op = cigar[c] & 15u;
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += cigar[c] >> 4;
-        }
-        const long long end = p + span;
-        const bool same = any ? (p == last_pos) : (tid == 0 && p == 0);
+        const long long end = p + (long long)ref_span(cigar_off, cigar, i);
+        const bool same = any ? (p == last_pos) : (tid0 && p == 0);
         any = true;
-        while (!live.empty() && live.top() < p) live.pop();
+        ring.expire_below(p);
         if (same) {
-            if (live.size() >= (size_t)maxcnt) continue;
-            if (end > p) { live.push(end); keep[i] = 1; }
+            if (ring.live >= (uint64_t)maxcnt) continue;
+            if (end > p) { ring.add(end); keep[i] = 1; }
         } else {
-            live.push(end); keep[i] = 1;
+            ring.add(end); keep[i] = 1;
         }
         last_pos = p;
     }
     return CLB_OK;
+}
+
+}  // namespace
+
+extern "C" int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
+                               const uint32_t *cigar_off, const uint32_t *cigar, uint8_t *keep) {
+    uint64_t max_span = 0;
+    for (uint64_t i = 0; i < n_reads; i++) max_span = std::max<uint64_t>(max_span, ref_span(cigar_off, cigar, i));
+    LiveRing ring; ring.init(max_span);
+    bool any = false; long long last_pos = -1;
+    return admit_range(maxcnt, 0, n_reads, pos, flag, cigar_off, cigar, keep, ring, any, last_pos, tid == 0, -1);
+}
+
+// Same result, in parallel.  The cap can only fire at record i when at least maxcnt records start within max_span
+// before it (live <= #{j < i : pos[j] + max_span >= pos[i]}), i.e. when pos[i - maxcnt] + max_span >= pos[i]: every other
+// record is admitted whatever happened before it (zero-span rule aside).  Flagged records form runs; a run is
+// replayed sequentially from the live set at its start, which consists of unflagged (hence known) records only once
+// runs whose look-back windows touch have been merged.  30x data has no flagged record at all; a uniformly deep contig
+// is one run and costs what clb_admit_reads costs.
+extern "C" int clb_admit_reads_mt(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
+                                  const uint32_t *cigar_off, const uint32_t *cigar, uint32_t max_ref_span, uint32_t n_threads,
+                                  uint8_t *keep, uint64_t *n_replayed) {
+    if (n_replayed) *n_replayed = 0;
+    if (n_reads == 0) return CLB_OK;
+    if (maxcnt == 0) { if (n_replayed) *n_replayed = n_reads; return clb_admit_reads(tid, maxcnt, n_reads, pos, flag, cigar_off, cigar, keep); }
+    // automatic thread count: all cores (at most 16) but at least 16384 records per thread; an explicit count is
+    // honoured down to 64 records per thread
+    if (n_threads == 0) n_threads = (uint32_t)std::min<uint64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), (n_reads + 16383) / 16384);
+    n_threads = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_threads, (n_reads + 63) / 64));
+    const uint64_t chunk = (n_reads + n_threads - 1) / n_threads;
+    auto parallel = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (uint32_t t = 1; t < n_threads; t++) th.emplace_back([&, t] { fn(t, std::min(n_reads, t * chunk), std::min(n_reads, (t + 1) * chunk)); });
+        fn(0, 0, std::min(n_reads, chunk));
+        for (auto &x : th) x.join();
+    };
+    const bool dbg_t = getenv("CLB_ADMIT_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    // pass 0: sortedness and (when the caller does not know it) the maximum reference span
+    std::vector<uint64_t> t_span(n_threads, 0);
+    std::vector<int> t_bad(n_threads, 0);
+    const bool need_span = max_ref_span == 0;
+    parallel([&](uint32_t t, uint64_t lo, uint64_t hi) {
+        uint64_t ms = 0; int bad = 0;
+        for (uint64_t i = lo; i < hi; i++) {
+            if (pos[i] < 0 || (i > 0 && pos[i] < pos[i - 1])) bad = 1;
+            if (need_span) ms = std::max<uint64_t>(ms, ref_span(cigar_off, cigar, i));
+        }
+        t_span[t] = ms; t_bad[t] = bad;
+    });
+    uint64_t max_span = max_ref_span;
+    for (uint32_t t = 0; t < n_threads; t++) {
+        max_span = std::max(max_span, t_span[t]);
+        if (t_bad[t]) { if (n_replayed) *n_replayed = n_reads; return clb_admit_reads(tid, maxcnt, n_reads, pos, flag, cigar_off, cigar, keep); }   // let the sequential pass judge
+    }
+    const double t1 = now();
+    // pass 1: unflagged records are decided on the spot; flagged ones are collected as runs [first, last]
+    struct Run { uint64_t first, last; };
+    std::vector<std::vector<Run>> t_runs(n_threads);
+    parallel([&](uint32_t t, uint64_t lo, uint64_t hi) {
+        std::vector<Run> &runs = t_runs[t];
+        for (uint64_t i = lo; i < hi; i++) {
+            const bool mapped = !(flag[i] & 0x4);
+            if (mapped && i >= maxcnt && (long long)pos[i - maxcnt] + (long long)max_span >= (long long)pos[i]) {
+                if (!runs.empty() && runs.back().last + 1 == i) runs.back().last = i; else runs.push_back({i, i});
+                keep[i] = 0;
+                continue;
+            }
+            uint8_t k = mapped ? 1 : 0;
+            // zero reference span?  Almost every record starts with a reference-consuming op: one load settles it.
+            bool zero = false;
+            if (mapped) {
+                const uint32_t c0 = cigar_off[i], c1 = cigar_off[i + 1];
+                const uint32_t v0 = c1 > c0 ? cigar[c0] : 0u;
+                zero = !(((0x18du >> (v0 & 15u)) & 1u) && (v0 >> 4)) && ref_span(cigar_off, cigar, i) == 0;
+            }
+            if (zero) {
+                // zero-span record: retained only when first at its position (relative to the previous mapped record)
+                long long j = (long long)i - 1;
+                while (j >= 0 && (flag[j] & 0x4)) j--;
+                if (j >= 0 ? pos[j] == pos[i] : (tid == 0 && pos[i] == 0)) k = 0;
+            }
+            keep[i] = k;
+        }
+    });
+    if (dbg_t) fprintf(stderr, "clb_admit_reads_mt: %u threads, pass0 %.3f s, pass1 %.3f s\n", n_threads, t1 - t0, now() - t1);
+    // merge runs whose look-back windows touch: run B depends on run A when a record of A can still be live at B's start
+    std::vector<Run> runs;
+    for (auto &v : t_runs) for (const Run &r : v) {
+        if (!runs.empty() && (runs.back().last + 1 == r.first || (long long)pos[runs.back().last] + (long long)max_span >= (long long)pos[r.first])) runs.back().last = r.last;
+        else runs.push_back(r);
+    }
+    if (runs.empty()) return CLB_OK;
+    uint64_t replayed = 0;
+    for (const Run &r : runs) replayed += r.last - r.first + 1;
+    if (n_replayed) *n_replayed = replayed;
+    // pass 2: replay the runs (in parallel over runs)
+    std::atomic<size_t> next{0};
+    std::atomic<int> rc_all{CLB_OK};
+    auto worker = [&] {
+        LiveRing ring; ring.init(max_span);
+        for (;;) {
+            const size_t ri = next.fetch_add(1);
+            if (ri >= runs.size()) break;
+            const Run &r = runs[ri];
+            ring.init(max_span);
+            // live set at the run's start: the records before it that can reach pos[first] (all decided in pass 1)
+            const long long p0 = pos[r.first];
+            uint64_t b = r.first;
+            while (b > 0 && (long long)pos[b - 1] + (long long)max_span >= p0) b--;
+            ring.low = p0;
+            bool any = false; long long last_pos = -1;
+            {   // previous mapped record (for the "first at this position" test)
+                long long j = (long long)r.first - 1;
+                while (j >= 0 && (flag[j] & 0x4)) j--;
+                any = j >= 0; last_pos = j >= 0 ? pos[j] : -1;
+            }
+            for (uint64_t j = b; j < r.first; j++) {
+                if (!keep[j]) continue;
+                const long long e = (long long)pos[j] + (long long)ref_span(cigar_off, cigar, j);
+                if (e >= p0) ring.add(e);
+            }
+            const int rc = admit_range(maxcnt, r.first, r.last + 1, pos, flag, cigar_off, cigar, keep, ring, any, last_pos, tid == 0, -1);
+            if (rc) rc_all = rc;
+        }
+    };
+    {
+        const uint32_t nt = (uint32_t)std::min<size_t>(n_threads, runs.size());
+        std::vector<std::thread> th;
+        for (uint32_t t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &x : th) x.join();
+    }
+    return rc_all;
 }
 
 extern "C" int clb_compact_reads(const clb_read_batch *in, const uint8_t *keep, int32_t *pos, uint16_t *flag, uint8_t *mapq,

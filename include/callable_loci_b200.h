@@ -165,6 +165,14 @@ int clb_debug_per_base(clb_ctx *ctx, uint32_t *raw, uint32_t *qc, uint32_t *low,
 int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
                     const uint32_t *cigar_off, const uint32_t *cigar, uint8_t *keep);
 
+/* Same result on n_threads host threads (0 = all cores, at most 16).  Only records that have at least maxcnt records
+ * starting within max_ref_span before them can be refused; the others are decided independently, the rest is replayed
+ * sequentially run by run.  max_ref_span: upper bound of any record's reference span (0 = compute it here).
+ * *n_replayed (may be NULL) receives how many records went through the sequential recurrence (0 on ordinary 30x data). */
+int clb_admit_reads_mt(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
+                       const uint32_t *cigar_off, const uint32_t *cigar, uint32_t max_ref_span, uint32_t n_threads,
+                       uint8_t *keep, uint64_t *n_replayed);
+
 /* Drop the records with keep[i] == 0 and repack the columns (what the host packer does after admission).
  * Output buffers must be at least as large as the inputs; offsets are rebased to start at 0.
  * out->n_reads / n_cigar / n_qual receive the compacted sizes. */

@@ -53,6 +53,43 @@ def test_admission_matches_oracle(seed):
             assert admit_reads(reads, maxcnt, tid).tolist() == oracle.admit(reads, maxcnt, tid).tolist()
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_parallel_admission_equals_sequential(seed):
+    """clb_admit_reads_mt == clb_admit_reads: sparse stretches (decided independently), deep piles (replayed runs),
+    runs that touch, zero-span records, placed-unmapped records, several thread counts."""
+    rng = np.random.default_rng(900 + seed)
+    recs = []
+    p = 0
+    for blk in range(int(rng.integers(3, 9))):
+        deep = rng.random() < 0.5
+        n = int(rng.integers(50, 400)) if deep else int(rng.integers(5, 60))
+        for _ in range(n):
+            p += int(rng.integers(0, 2 if deep else 40))
+            kind = rng.random()
+            cig = "30M" if kind < 0.7 else ("10M5D15M" if kind < 0.8 else ("12S" if kind < 0.9 else "5M2I20M"))
+            flag = 4 if rng.random() < 0.05 else 0
+            recs.append((p, flag, 60, cig, 30, f"r{len(recs)}"))
+        p += int(rng.integers(0, 200))
+    reads = ReadColumns.from_records(recs)
+    for maxcnt in (1, 3, 8, 50):
+        for tid in (0, 1):
+            want = admit_reads(reads, maxcnt, tid)
+            assert want.tolist() == oracle.admit(reads, maxcnt, tid).tolist()
+            for threads, span in ((1, 0), (3, 0), (8, 35), (0, 1000)):
+                st = {}
+                got = admit_reads(reads, maxcnt, tid, threads=threads, max_ref_span=span, stats=st)
+                assert got.tolist() == want.tolist(), (maxcnt, tid, threads, span)
+
+
+def test_parallel_admission_sparse_data_replays_nothing():
+    from decodingustools_b200 import synth
+    c = synth.synth_short("chr22", 400_000, seed=3)
+    st = {}
+    keep = admit_reads(c.reads, 500, 0, threads=4, stats=st)
+    assert st["replayed"] == 0 and keep.tolist() == admit_reads(c.reads, 500, 0).tolist()
+    assert np.array_equal(keep, (c.reads.flag & 4) == 0)
+
+
 def test_admission_rejects_unsorted():
     reads = ReadColumns.from_records([(5, 0, 60, "3M", 30), (2, 0, 60, "3M", 30)])
     with pytest.raises(_lib.ClbError):
