@@ -13,9 +13,12 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 static const char *kStateName[6] = {"REF_N", "CALLABLE", "NO_COVERAGE", "LOW_COVERAGE", "EXCESSIVE_COVERAGE", "POOR_MAPPING_QUALITY"};
 
@@ -268,6 +271,8 @@ struct clb_bed_writer {
     std::string pend_name;
     clb_interval pend{};
     std::vector<char> buf;
+    struct Part { std::unique_ptr<char[]> p; size_t cap = 0; };
+    std::vector<Part> parts;                // per-thread formatting buffers of large contigs (reused, never zero-filled)
     void put(const char *s, size_t n) {
         if (in_memory) mem.append(s, n);
         else {
@@ -283,6 +288,19 @@ static inline char *put_u32(char *p, uint32_t v) {
     do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
     while (n) *p++ = tmp[--n];
     return p;
+}
+
+static const uint8_t kStateLen[6] = {5, 8, 11, 12, 18, 20};
+// decimal text of v, two digits per step
+static inline char *put_u32_fast(char *p, uint32_t v) {
+    static const char D[201] =
+        "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+        "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+    const int nd = v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+    char *e = p + nd, *q = e;
+    while (v >= 100u) { const uint32_t r = v % 100u; v /= 100u; q -= 2; q[0] = D[2 * r]; q[1] = D[2 * r + 1]; }
+    if (v >= 10u) { q -= 2; q[0] = D[2 * v]; q[1] = D[2 * v + 1]; } else { *--q = (char)('0' + v); }
+    return e;
 }
 
 static void write_line(clb_bed_writer *w, const std::string &name, const clb_interval &iv) {
@@ -339,9 +357,68 @@ extern "C" int clb_bed_writer_add_contig(clb_bed_writer *w, const char *name, ui
             }
         }
     }
-    for (uint64_t i = 0; i < n_iv; i++) {
-        write_line(w, nm, iv[i]);
-        if (binned_state(iv[i].state)) any_range = true;
+    if (n_iv < (1u << 16)) {
+        for (uint64_t i = 0; i < n_iv; i++) {
+            write_line(w, nm, iv[i]);
+            if (binned_state(iv[i].state)) any_range = true;
+        }
+    } else {
+        // large contigs: format on several threads, each into its own reusable buffer, then copy / pwrite the parts to
+        // their final offsets in parallel (BED text of a 30x human chromosome is ~100 MB)
+        const uint32_t nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const bool dbg_t = getenv("CLB_ADMIT_DEBUG") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
+        if (w->parts.size() < nt) w->parts.resize(nt);
+        std::vector<size_t> sizes(nt, 0);
+        std::vector<int> binned(nt, 0);
+        const uint64_t per = (n_iv + nt - 1) / nt;
+        const size_t max_line = nm.size() + 1 + 10 + 1 + 10 + 1 + 20 + 1;
+        auto run_threads = [&](auto &&fn) {
+            std::vector<std::thread> th;
+            for (uint32_t t = 1; t < nt; t++) th.emplace_back(fn, t);
+            fn(0);
+            for (auto &x : th) x.join();
+        };
+        run_threads([&](uint32_t t) {
+            const uint64_t lo = std::min(n_iv, t * per), hi = std::min(n_iv, lo + per);
+            clb_bed_writer::Part &out = w->parts[t];
+            if (out.cap < (size_t)(hi - lo) * max_line) { out.cap = (size_t)(hi - lo) * max_line; out.p.reset(new char[out.cap]); }
+            char *p = out.p.get();
+            int any = 0;
+            for (uint64_t i = lo; i < hi; i++) {
+                memcpy(p, nm.data(), nm.size()); p += nm.size();
+                *p++ = '\t'; p = put_u32_fast(p, iv[i].start); *p++ = '\t'; p = put_u32_fast(p, iv[i].end); *p++ = '\t';
+                const uint8_t st = iv[i].state;
+                memcpy(p, kStateName[st], kStateLen[st]); p += kStateLen[st]; *p++ = '\n';
+                any |= binned_state(st) ? 1 : 0;
+            }
+            sizes[t] = (size_t)(p - out.p.get()); binned[t] = any;
+        });
+        const double t1 = now();
+        std::vector<size_t> off(nt + 1, 0);
+        for (uint32_t t = 0; t < nt; t++) { off[t + 1] = off[t] + sizes[t]; if (binned[t]) any_range = true; }
+        if (w->in_memory) {
+            const size_t base = w->mem.size();
+            w->mem.resize(base + off[nt]);
+            run_threads([&](uint32_t t) { memcpy(&w->mem[base + off[t]], w->parts[t].p.get(), sizes[t]); });
+        } else {
+            w->flush(); fflush(w->fp);
+            const off_t base = ftello(w->fp);
+            const int fd = fileno(w->fp);
+            std::atomic<int> io_err{0};
+            run_threads([&](uint32_t t) {
+                size_t done = 0;
+                while (done < sizes[t]) {
+                    const ssize_t r = pwrite(fd, w->parts[t].p.get() + done, sizes[t] - done, base + (off_t)(off[t] + done));
+                    if (r <= 0) { io_err = 1; break; }
+                    done += (size_t)r;
+                }
+            });
+            if (io_err) return CLB_E_IO;
+            fseeko(w->fp, base + (off_t)off[nt], SEEK_SET);
+        }
+        if (dbg_t) fprintf(stderr, "clb_bed_writer_add_contig: %u threads, format %.3f s, output %.3f s (%zu bytes)\n", nt, t1 - t0, now() - t1, off[nt]);
     }
     if (n_iv) { w->have_pending = true; w->pend_name = nm; w->pend = iv[n_iv - 1]; }
     if (has_bins) *has_bins = any_range ? 1 : 0;
