@@ -3,23 +3,32 @@
 
 Contract (driver): `python bench.py --gpus N --steps K --warmup W` (torchrun for N > 1) prints ONE JSON line.
 A "step" is one pass of the hot path over one contig-sized batch of synthetic reads:
-    N = 1 : BASELINE.json configs[1] -- chr1-size contig (248.96 Mbp), synthetic 30x 2x150 bp, one B200.
-    N > 1 : every rank owns one chr1-size region shard of an N x chr1 genome (weak scaling); the only
-            collective is the all-reduce of the additive counters/bins (NCCL via torch.distributed).
-`value`  : pileup cells (aligned bases = sum of raw depth) per second, inputs resident in HBM.
-`e2e`    : same metric through the public C-ABI call sequence with HOST (pinned) column buffers: reference upload,
-           column-batch H2D copies, kernels, D2H of intervals + counters, all inside the timed region.
+    workload : BASELINE.json configs[1] -- chr1-size contig (248.96 Mbp), synthetic 30x 2x150 bp.
+    N = 1    : one B200.
+    N > 1    : every rank runs the same chr1-size contig on its own GPU (weak scaling: per-GPU work fixed); the counters of
+               the N replicas are summed with the library's own NCCL all-reduce (clb_allreduce_nccl) inside the step and
+               checked (= N x the single-GPU counters).  The `strong` block cuts ONE chr1 into N region shards (halo
+               reads, all-reduce of counters/bins, interval stitching on rank 0) and checks the stitched result against
+               rank 0's single-GPU run of the whole contig.
+`value`  : pileup cells (aligned bases = sum of raw depth) per second, inputs resident in HBM: window ranges + pileup
+           kernels + interval compaction (+ all-reduce); the upload-time helper kernels are reported beside it.
+`e2e`    : the same metric through the public C-ABI call sequence from HOST buffers, everything the CPU arm also pays
+           inside the timed region: read admission (htslib depth cap, clb_admit_reads_mt), reference upload, column-batch
+           H2D copies, kernels, D2H of intervals + counters, and the BED text written to a real file.
 `--impl reference`: the CPU oracle (restatement of the reference's single-threaded loop; the Rust reference itself
            cannot be built in this image) timed on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
+import hashlib
 import json
 import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -30,6 +39,7 @@ if ROOT not in sys.path:
 
 METRIC = "aligned Gbases/s CallableLoci pileup"
 UNIT = "Gbases/s"
+WORKLOAD = "chr1-size synthetic 30x 2x150bp PE, pileup+classify+BED on one B200 per rank (BASELINE configs[1])"
 
 
 def parse_args():
@@ -40,8 +50,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the contig (1.0 = chr1, 248.96 Mbp)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-mbp", type=float, default=48.0, help="oracle sample for cpu_baseline (Mbp of the contig; about 12 s of CPU work)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-mbp", type=float, default=48.0, help="oracle sample of the bounded CPU legs (Mbp of the contig)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU oracle leg (cpu_baseline, parity)")
+    ap.add_argument("--no-parity-full", action="store_true", help="check parity on the bounded sample only, not on the whole contig")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the reduced-scale runs of BASELINE configs 4/4b/5")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the region-sharded strong-scaling leg")
     ap.add_argument("--batch-reads", type=int, default=4_000_000, help="column-batch size of the e2e leg")
     return ap.parse_args()
 
@@ -54,6 +67,19 @@ def load_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(scale, world):
+    """dram__bytes_read + dram__bytes_write of ONE launch of the dominant kernel, from the ncu --set full capture of this
+    workload summarised under profiles/ (never a literal in this file); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "r02_k_pileup_fast_traffic.json")
+    if scale != 1.0 or world != 1 or not os.path.exists(p):
+        return None, ("profiles/r02_k_pileup_fast_traffic.json" if os.path.exists(p) else None)
+    try:
+        d = json.load(open(p))
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"]), "profiles/r02_k_pileup_fast_traffic.json"
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -71,10 +97,8 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
             self._nv = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(gpu_index))
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self._h = None
@@ -115,38 +139,64 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
-def make_workload(scale: float, rank: int, device):
-    """chr1-size synthetic contig for this rank (seed differs per rank), admission-filtered and packed."""
+def physical_gpu_index(local_index: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        parts = vis.split(",")
+        if local_index < len(parts) and parts[local_index].strip().isdigit():
+            return int(parts[local_index])
+    return local_index
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Run this rank on the cores of its GPU's NUMA node, so that the column buffers it allocates (first touch) and
+    page-locks live next to the GPU's PCIe root.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(local_rank))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for this GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cores": len(cpus)}
+    except Exception as e:      # binding is an optimisation, never a failure
+        return {"numa_node": None, "note": f"not bound: {type(e).__name__}"}
+
+
+def make_workload(scale: float, device=None):
+    """The chr1-size synthetic contig (same seed on every rank), unfiltered, as the decoder would hand it over."""
     from decodingustools_b200 import synth
-    from decodingustools_b200.callable_loci import admit_reads, compact_reads
     from decodingustools_b200.options import CallableOptions
     opt = CallableOptions()
     length = max(100_000, int(synth.HG38["chr1"] * scale))
     t0 = time.time()
-    c = synth.synth_short("chr1", length, synth.SEED0 + 1 + 1000 * rank, qual_device=device)
-    t_gen = time.time() - t0
-    t0 = time.time()
-    keep = admit_reads(c.reads, opt.pileup_max_depth, 0)
-    cells = int(c.reads.ref_len()[keep].sum())
-    if np.array_equal(keep, (c.reads.flag & 4) == 0):
-        reads = c.reads          # only placed-unmapped records were refused: the kernel skips FLAG 0x4 itself, no repacking needed
-    else:
-        reads = compact_reads(c.reads, keep)
-    t_admit = time.time() - t0
-    return opt, c, reads, cells, {"synth_s": round(t_gen, 2), "host_admission_s": round(t_admit, 2)}
+    c = synth.synth_short("chr1", length, synth.SEED0 + 1, qual_device=device)     # the generator may fill the quality column on the GPU
+    return opt, c, {"synth_s": round(time.time() - t0, 2)}
 
 
-def oracle_sample(c, reads_unfiltered, opt, sample_bp: int):
-    """Bounded CPU sample: the first sample_bp bases of the contig with every read that starts inside."""
+def oracle_run(c, reads, opt, length: int):
+    """The CPU oracle over the first `length` bases of the contig (every read that starts inside)."""
     from oracle import oracle
-    sample_bp = min(sample_bp, c.length)
-    hi = int(np.searchsorted(reads_unfiltered.pos, sample_bp - 200, side="left"))
-    sub = reads_unfiltered.slice(0, hi)
+    length = min(length, c.length)
+    if length < c.length:
+        hi = int(np.searchsorted(reads.pos, length - 200, side="left"))
+        reads = reads.slice(0, hi)
     t0 = time.perf_counter()
-    run = oracle.OracleRun(opt, sample_bp)
-    oc = run.process_contig(c.name, 0, sample_bp, c.ref[:sample_bp], sub)
+    run = oracle.OracleRun(opt, length)
+    oc = run.process_contig(c.name, 0, length, c.ref[:length], reads)
     dt = time.perf_counter() - t0
-    return oc, run, dt, sub
+    return oc, run, dt, reads
 
 
 def run_reference(args, rank, world):
@@ -161,7 +211,7 @@ def run_reference(args, rank, world):
     c = synth.synth_short("chr1", length, synth.SEED0 + 1)
     times, cells = [], 0
     for i in range(args.warmup + args.steps):
-        oc, _, dt, _ = oracle_sample(c, c.reads, opt, sample_bp)
+        oc, _, dt, _ = oracle_run(c, c.reads, opt, sample_bp)
         if i >= args.warmup:
             times.append(dt)
         cells = oc.summed_coverage
@@ -171,16 +221,97 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
-        "config": {"workload": "chr1-size synthetic 30x 2x150bp PE (BASELINE configs[1]); CPU arm runs a bounded sample",
+        "config": {"workload": WORKLOAD + "; the CPU arm runs a bounded prefix of it (a rate, so comparable)",
                    "sample_bp": sample_bp, "sample_cells": int(cells)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"first {sample_bp} bp of the contig ({int(cells)} cells) per step; oracle/callable_oracle.c, "
-                                   "single thread like the reference (src/api/coverage.rs:232-234); omits the reference's per-base "
-                                   "faidx call and per-cell qname hashing, so it is faster than the real binary"},
+                                   "single thread like the reference (src/api/coverage.rs:232-234), admission and BED text included; omits "
+                                   "the reference's per-base faidx call and per-cell qname hashing, so it is faster than the real binary"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class Pinned:
+    """A numpy array page-locked in place (the e2e leg streams from it; no second host copy)."""
+
+    def __init__(self, rt, arr):
+        self.arr, self._rt = arr, rt
+        rc = rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+
+    def data_ptr(self):
+        return self.arr.ctypes.data
+
+
+class Nccl:
+    """An ncclComm_t of our own over the ranks of the job, created through ctypes on the NCCL build torch loaded (the
+    unique id travels through torch.distributed), so that the library's clb_allreduce_nccl is what reduces."""
+
+    class _Uid(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+
+    def __init__(self, rank, world, dev):
+        import torch
+        import torch.distributed as dist
+        path = None
+        for ln in open("/proc/self/maps"):
+            if "libnccl" in ln and ".so" in ln:
+                path = ln.split()[-1]
+                break
+        self.lib = C.CDLL(path or "libnccl.so.2", mode=C.RTLD_GLOBAL)
+        self.path = path or "libnccl.so.2"
+        uid = Nccl._Uid()
+        if rank == 0:
+            self._ok(self.lib.ncclGetUniqueId(C.byref(uid)))
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        self.comm = C.c_void_p(0)
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, Nccl._Uid, C.c_int]
+        self._ok(self.lib.ncclCommInitRank(C.byref(self.comm), world, uid, rank))
+        self.allreduce_fn = C.cast(self.lib.ncclAllReduce, C.c_void_p).value
+        ver = C.c_int(0)
+        self.lib.ncclGetVersion(C.byref(ver))
+        self.version = ver.value
+
+    @staticmethod
+    def _ok(rc):
+        if rc != 0:
+            raise RuntimeError(f"NCCL call failed: {rc}")
+
+    def close(self):
+        try:
+            self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+            self.lib.ncclCommDestroy(self.comm)
+        except Exception:
+            pass
+
+
+def kernel_config_run(tag, c, opt, peak):
+    """One reduced-scale BASELINE config: admission, upload, then the HBM-resident kernel time (best of 4 re-runs)."""
+    from decodingustools_b200.callable_loci import CallableLociContext, admit_reads, compact_reads
+    t0 = time.perf_counter()
+    st = {}
+    keep = admit_reads(c.reads, opt.pileup_max_depth, 0, threads=0, stats=st)
+    reads = compact_reads(c.reads, keep)
+    t_adm = time.perf_counter() - t0
+    ctx = CallableLociContext(opt)
+    ctx.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
+    ctx.push_reads(reads)
+    r = ctx.finish_contig(copy_intervals=False)
+    runs = [ctx.rerun_resident(fetch=True) for _ in range(4)]
+    best = min(runs, key=lambda x: x[1].pileup_ms)
+    step_ms, res = best
+    byts = reads.nbytes_device() + c.length // 8
+    ctx.close()
+    return {"config": tag, "contig_bp": c.length, "reads_offered": c.reads.n, "reads_admitted": reads.n, "cigar_ops": reads.n_cigar,
+            "cells": int(r.summed_coverage), "pileup_ms": round(res.pileup_ms, 4), "step_ms": round(step_ms, 4),
+            "upload_kernels_ms": round(r.upload_ms, 4), "general_windows": int(res.general_windows),
+            "Gbases_s": round(r.summed_coverage / res.pileup_ms / 1e6, 1), "frac": round(byts / res.pileup_ms / 1e6 / peak, 4),
+            "host_admission_s": round(t_adm, 2), "admission_replayed": st.get("replayed")}
 
 
 def main():
@@ -191,9 +322,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None      # before any buffer of this rank is allocated
+
     import torch
     import torch.distributed as dist
-    from decodingustools_b200.callable_loci import CallableLociContext
+    from decodingustools_b200 import _lib, sharding
+    from decodingustools_b200.callable_loci import (INTERVAL_DTYPE, CallableLociContext, _result, admit_reads, compact_reads)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -202,70 +336,90 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    peak, peak_src = load_peak()
 
-    opt, c, reads, cells_expected, prep = make_workload(args.scale, rank, dev)
-    alg_bytes = reads.nbytes_device() + c.length // 8          # packed columns + 1 bit per reference base
+    opt, c, prep = make_workload(args.scale, dev)
+    reads = c.reads                                   # unfiltered: admission is part of the e2e step
     span = reads.max_ref_span()
+    maxcnt = opt.pileup_max_depth
+    alg_bytes = reads.nbytes_device() + c.length // 8          # packed columns + 1 bit per reference base
 
-    # page-lock the column buffers in place (the e2e leg streams from them; no second host copy)
     rt = torch.cuda.cudart()
-    class _Pinned:
-        def __init__(self, arr):
-            self.arr = arr
-            rc = rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
-            if int(rc) != 0:
-                raise RuntimeError(f"cudaHostRegister failed: {rc}")
-        def data_ptr(self):
-            return self.arr.ctypes.data
-    cols = {k: _Pinned(getattr(reads, k)) for k in ("pos", "flag", "mapq", "cigar", "qual")}
-    ref_pinned = _Pinned(c.ref)
+    cols = {k: Pinned(rt, getattr(reads, k)) for k in ("pos", "flag", "mapq", "cigar", "qual")}
+    ref_pinned = Pinned(rt, c.ref)
+    cig_off = reads.cigar_off.astype(np.int64); q_off = reads.qual_off.astype(np.int64)
+    batches = []                                      # column batches as a decoder thread would emit them (batch-relative offsets)
+    for lo in range(0, reads.n, args.batch_reads):
+        hi = min(reads.n, lo + args.batch_reads)
+        co = Pinned(rt, np.ascontiguousarray((cig_off[lo:hi + 1] - cig_off[lo]).astype(np.uint32)))
+        qo = Pinned(rt, np.ascontiguousarray((q_off[lo:hi + 1] - q_off[lo]).astype(np.uint64)))
+        batches.append((lo, hi, co, qo))
 
     ctx = CallableLociContext(opt, device=local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-
-    cig_off = reads.cigar_off.astype(np.int64); q_off = reads.qual_off.astype(np.int64)
-    # column batches as a decoder thread would emit them: batch-relative offset columns, page-locked
-    batches = []
-    for lo in range(0, reads.n, args.batch_reads):
-        hi = min(reads.n, lo + args.batch_reads)
-        co = _Pinned(np.ascontiguousarray((cig_off[lo:hi + 1] - cig_off[lo]).astype(np.uint32)))
-        qo = _Pinned(np.ascontiguousarray((q_off[lo:hi + 1] - q_off[lo]).astype(np.uint64)))
-        batches.append((lo, hi, co, qo))
+    bed_dir = tempfile.mkdtemp(prefix="clb_bench_")
+    bed_path = os.path.join(bed_dir, f"callable_regions.rank{rank}.bed")
+    mapped_only = None
 
     def e2e_pass():
-        """Public call sequence with host buffers: begin (reference upload) -> column batches -> finish (D2H)."""
-        ctx._check(ctx._L.clb_begin_contig(ctx._h, 0, b"chr1", c.length, ref_pinned.data_ptr(), c.length, 0, c.length, 0, c.length, span))
+        """What `coverage` does for one contig, from host buffers to the BED file."""
+        nonlocal mapped_only
+        t0 = time.perf_counter()
+        st = {}
+        keep = admit_reads(reads, maxcnt, 0, threads=0, max_ref_span=span, stats=st)
+        if mapped_only is None:
+            mapped_only = (reads.flag & 4) == 0
+        if not np.array_equal(keep, mapped_only):
+            raise SystemExit("the depth cap refused records of the 30x workload: this leg expects to stream the page-locked columns as they are")
+        t1 = time.perf_counter()
+        # only placed-unmapped records were refused: the kernels skip FLAG 0x4 themselves, no repacking needed
+        ctx._check(L.clb_begin_contig(ctx._h, 0, b"chr1", c.length, ref_pinned.data_ptr(), c.length, 0, c.length, 0, c.length, span))
         ctx.reserve(reads.n, reads.n_cigar, reads.n_qual)
         for lo, hi, co, qo in batches:
             ctx.push_raw(hi - lo, int(cig_off[hi] - cig_off[lo]), int(q_off[hi] - q_off[lo]),
                          cols["pos"].data_ptr() + 4 * lo, cols["flag"].data_ptr() + 2 * lo, cols["mapq"].data_ptr() + lo,
                          co.data_ptr(), cols["cigar"].data_ptr() + 4 * int(cig_off[lo]), qo.data_ptr(),
                          cols["qual"].data_ptr() + int(q_off[lo]))
-        return ctx.finish_contig(copy_intervals=False)
+        raw = ctx.finish_contig_raw()
+        t2 = time.perf_counter()
+        w = L.clb_bed_writer_open(bed_path.encode(), c.length)
+        bins = np.ctypeslib.as_array(raw.bins, shape=(3 * int(raw.n_bins),)).copy()
+        has = C.c_int(0)
+        rc = L.clb_bed_writer_add_contig(w, b"chr1", c.length, raw.intervals, raw.n_intervals, bins.ctypes.data_as(C.c_void_p),
+                                         raw.n_bins, raw.stride, C.byref(has))
+        rc2 = L.clb_bed_writer_close(w)
+        t3 = time.perf_counter()
+        if rc or rc2:
+            raise SystemExit(f"BED writer failed: {rc} {rc2}")
+        return raw, {"admission_ms": 1e3 * (t1 - t0), "device_pipeline_ms": 1e3 * (t2 - t1), "bed_write_ms": 1e3 * (t3 - t2),
+                     "total_ms": 1e3 * (t3 - t0), "admission_replayed": st.get("replayed")}
 
-    keepalive: list = []
-    first = e2e_pass()                      # also leaves the contig resident for the HBM-resident leg
-    # size-independent properties of the full-size result (the oracle only sees a bounded sample, below)
-    assert first.summed_coverage == cells_expected, (first.summed_coverage, cells_expected)
+    raw_first, _ = e2e_pass()                # also leaves the contig resident for the HBM-resident leg
+    first = _result(raw_first, True)
+    cells = int(first.summed_coverage)
+    upload_ms = float(first.upload_ms)
+    # size-independent properties of the full-size result
+    assert cells == int(reads.ref_len()[(reads.flag & 4) == 0].sum()), "summed coverage != aligned bases of the admitted reads"
     assert int(first.state_counts.sum()) == c.length
-    _, chk = ctx.rerun_resident(fetch=True, copy_intervals=True)
-    iv = chk.intervals
+    iv = first.intervals
     assert iv["start"][0] == 0 and iv["end"][-1] == c.length and np.array_equal(iv["start"][1:], iv["end"][:-1])
     assert np.all(iv["state"][1:] != iv["state"][:-1])
     assert np.array_equal(np.bincount(iv["state"], weights=(iv["end"] - iv["start"]).astype(np.float64), minlength=6).astype(np.int64),
-                          chk.state_counts.astype(np.int64))
-    assert int(chk.bins.sum()) == int(chk.state_counts[0] + chk.state_counts[1] + chk.state_counts[5])
-    n_intervals = int(iv.shape[0]); del iv, chk
+                          first.state_counts.astype(np.int64))
+    assert int(first.bins.sum()) == int(first.state_counts[0] + first.state_counts[1] + first.state_counts[5])
+    n_intervals = int(iv.shape[0])
+    gpu_bed_sha = hashlib.sha256(open(bed_path, "rb").read()).hexdigest()
+
+    nccl = None
+    if world > 1:
+        nccl = Nccl(rank, world, dev)
+        L.clb_set_nccl_allreduce(C.c_void_p(nccl.allreduce_fn))
 
     def allreduce_counters():
-        if world == 1:
-            return
-        ptr, n = ctx.counters_device()
-        class _Wrap:     # torch tensor aliasing the library's counter buffer (uint64 sums == int64 sums bitwise)
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
-        t = torch.as_tensor(_Wrap(), device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if nccl is not None:
+            ctx.allreduce_nccl(nccl.comm.value)
 
     # ---------------- HBM-resident leg: W warm-up + K timed steps, barrier + sync on both sides
     for _ in range(args.warmup):
@@ -288,79 +442,182 @@ def main():
         dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
+    allreduce_ok = None
+    if world > 1:
+        summed = ctx.refresh_counters()          # the last step's counters, all-reduced: N identical replicas
+        allreduce_ok = bool(np.array_equal(summed.state_counts, first.state_counts * np.uint64(world))
+                            and summed.summed_coverage == world * first.summed_coverage and summed.summed_baseq == world * first.summed_baseq
+                            and np.array_equal(summed.bins.astype(np.uint64), first.bins.astype(np.uint64) * np.uint64(world)))
     _, res = ctx.rerun_resident(fetch=True)
-    pileup_ms = res.pileup_ms
+    pileup_ms, fast_ms, general_windows = res.pileup_ms, res.fast_ms, res.general_windows
     launches_per_step = res.gpu_launches
 
-    # ---------------- end-to-end leg through the public API with host buffers
-    e2e_ms = []
-    r = first
+    # ---------------- end-to-end leg through the public API with host buffers (admission and BED text inside)
+    e2e_runs = []
+    raw = raw_first
     for i in range(args.e2e_steps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        r = e2e_pass()
+        raw, tm = e2e_pass()
         allreduce_counters()
         torch.cuda.synchronize()
-        e2e_ms.append(1e3 * (time.perf_counter() - t0))
-    h2d_bytes, d2h_bytes = r.h2d_bytes, r.d2h_bytes
-    e2e_best = min(e2e_ms) if e2e_ms else float("nan")
+        e2e_runs.append(tm)
+    e2e_best = min(e2e_runs, key=lambda t: t["total_ms"]) if e2e_runs else {"total_ms": float("nan")}
+    h2d_bytes, d2h_bytes, h2d_dev_ms = int(raw.h2d_bytes), int(raw.d2h_bytes), float(raw.h2d_ms)
+    e2e_best_ms = e2e_best["total_ms"]
+
+    # ---------------- strong scaling: ONE chr1 cut into N region shards (halo reads, all-reduce, stitching, parity)
+    strong = None
+    if world > 1 and not args.no_strong:
+        window = int(L.clb_window_positions())
+        plan = sharding.plan_regions([c.length], world, window)[rank]
+        sh = plan[0]
+        lo, hi = sharding.reads_for_region(reads, sh.start, sh.end, span)
+        sub = reads.slice(lo, hi)
+        # admission was decided for the whole contig above (nothing but placed-unmapped records refused; the kernels skip those)
+        ctx2 = CallableLociContext(opt, device=local_rank)
+        ctx2.set_stream(stream.cuda_stream)
+        ctx2.begin_contig(0, "chr1", c.length, c.ref, c.length, region=(sh.start, sh.end), max_ref_span=span)
+        ctx2.push_reads(sub)
+        part = ctx2.finish_contig()
+        for _ in range(args.warmup):
+            ctx2.rerun_resident(fetch=False); ctx2.allreduce_nccl(nccl.comm.value)
+        torch.cuda.synchronize(); dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            ctx2.rerun_resident(fetch=False); ctx2.allreduce_nccl(nccl.comm.value)
+        s1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        strong_ms = s0.elapsed_time(s1) / args.steps
+        tot = ctx2.refresh_counters()
+        stitched = sharding.gather_and_stitch(part.intervals, sh.start, dst=0)
+        t_strong = torch.tensor([strong_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_strong, op=dist.ReduceOp.MAX)
+        ok = None
+        if rank == 0:
+            ok = bool(np.array_equal(stitched[["start", "end", "state"]], first.intervals[["start", "end", "state"]])
+                      and np.array_equal(tot.state_counts, first.state_counts) and tot.summed_coverage == first.summed_coverage
+                      and tot.summed_baseq == first.summed_baseq and tot.summed_mapq == first.summed_mapq
+                      and tot.quality_bases == first.quality_bases and tot.n_covered_bases == first.n_covered_bases
+                      and np.array_equal(tot.bins, first.bins))
+        strong = {"workload": f"the same chr1-size contig cut into {world} region shards (window-aligned), one per GPU",
+                  "ms_per_step": float(t_strong[0]), "value": cells / (float(t_strong[0]) * 1e-3) / 1e9, "unit": UNIT,
+                  "shard_reads": int(sub.n), "shard_bp": int(sh.end - sh.start), "sharded_parity": ok,
+                  "exchange": "clb_allreduce_nccl (ncclAllReduce sum of 12 counters + 3 x n_bins bins, uint64) inside the step; interval "
+                              "lists gathered and stitched on rank 0 outside it"}
+        ctx2.close()
 
     # ---------------- max over ranks
-    t_total = torch.tensor([total_ms, e2e_best, float(cells_expected)], dtype=torch.float64, device=dev)
+    t_total = torch.tensor([total_ms, e2e_best_ms, float(cells), h2d_bytes / max(h2d_dev_ms, 1e-9) / 1e6], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t_total.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t_total.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_best, cells_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        tmin = t_total.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        total_ms, e2e_best_ms, cells_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        h2d_rank_gbs = {"min": float(tmin[3]), "max": float(tmax[3])}
     else:
-        cells_all = float(cells_expected)
+        cells_all = float(cells)
+        h2d_rank_gbs = {"min": float(t_total[3]), "max": float(t_total[3])}
 
     if rank == 0:
-        peak, peak_src = load_peak()
         ms_per_step = total_ms / args.steps
         value = cells_all / (ms_per_step * 1e-3) / 1e9
         achieved = alg_bytes / (pileup_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE resident launch on the default workload, from the ncu --set full
-        # capture summarised in profiles/r01_k_pileup_classify_resident_chr1.txt (same seed, same launch)
-        traffic = 8_922_642_000 if (args.scale == 1.0 and world == 1) else None
+        traffic, traffic_src = load_traffic(args.scale, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u32 integer", "data": "synthetic",
-            "config": {"workload": "chr1-size synthetic 30x 2x150bp PE, pileup+classify+BED on one B200 per rank (BASELINE configs[1])",
-                       "contig_bp": c.length, "reads": reads.n, "cells_per_rank": cells_expected, "bed_intervals": n_intervals, "scale": args.scale,
+            "config": {"workload": WORKLOAD, "contig_bp": c.length, "reads": reads.n, "cells_per_rank": cells, "bed_intervals": n_intervals,
+                       "scale": args.scale,
                        "l2_policy": f"inputs ({alg_bytes / 1e9:.2f} GB per step) are far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"region shards x{world}, counters all-reduced" if world > 1 else "single GPU", **prep},
+                       "parallelism": (f"{world} replicas of the contig, one per GPU, counters summed by clb_allreduce_nccl; see `strong` for the region-sharded run"
+                                       if world > 1 else "single GPU"), **prep},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_pileup_classify", "kernel_ms": pileup_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_cell": alg_bytes / cells_expected, "peak_source": peak_src},
-            "e2e": {"value": cells_all / (e2e_best * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_best, "h2d_device_ms": round(float(r.h2d_ms), 2),
-                    "note": "clb_begin_contig + clb_push_reads batches from pinned host columns + clb_finish_contig (D2H); PCIe-bound"},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "k_pileup_fast (+ k_pileup_general for the windows it hands over)", "kernel_ms": pileup_ms,
+                         "k_pileup_fast_ms": fast_ms, "general_windows": int(general_windows),
+                         "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_cell": alg_bytes / cells, "peak_source": peak_src},
+            "upload_kernels_ms": round(upload_ms, 3),
+            "upload_kernels_note": "k_validate_batch + k_rebase_batch per column batch and k_nmask_from_ascii per contig run once at upload, "
+                                   "outside the resident step `value` times (inside `e2e`)",
+            "e2e": {"value": cells_all / (e2e_best_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_best_ms,
+                    "admission_ms": round(e2e_best.get("admission_ms", float("nan")), 2),
+                    "device_pipeline_ms": round(e2e_best.get("device_pipeline_ms", float("nan")), 2),
+                    "bed_write_ms": round(e2e_best.get("bed_write_ms", float("nan")), 2),
+                    "admission_replayed_reads": e2e_best.get("admission_replayed"),
+                    "h2d_device_ms": round(h2d_dev_ms, 2), "h2d_GBps_per_rank": h2d_rank_gbs,
+                    "bed_bytes": os.path.getsize(bed_path),
+                    "note": "per contig: clb_admit_reads_mt (htslib depth cap) + clb_begin_contig + clb_push_reads batches from page-locked host "
+                            "columns + clb_finish_contig (D2H) + clb_bed_writer_* to a real file; the device part is PCIe-bound"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "kernel_step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
         }
+        if world > 1:
+            line["allreduce_verified"] = allreduce_ok
+            line["nccl"] = {"library": nccl.path, "version": nccl.version}
+            line["numa"] = numa
+            if strong is not None:
+                line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
-            from decodingustools_b200 import synth
-            sample_bp = int(min(args.cpu_sample_mbp * 1e6, c.length))
-            oc, orun, dt, sub = oracle_sample(c, c.reads, opt, sample_bp)
+            full = not args.no_parity_full
+            sample_bp = c.length if full else int(min(args.cpu_sample_mbp * 1e6, c.length))
+            oc, orun, dt, sub = oracle_run(c, reads, opt, sample_bp)
             line["cpu_baseline"] = {
                 "value": oc.summed_coverage / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"first {sample_bp} bp of the same contig ({oc.summed_coverage} cells, {dt:.1f} s); oracle/callable_oracle.c "
-                          f"single-threaded like the reference; host has {os.cpu_count()} cores"}
-            # size-independent sanity of the full-size GPU result + exact parity on the sample prefix
-            ctx.begin_contig(0, "chr1", sample_bp, c.ref[:sample_bp], sample_bp, max_ref_span=span)
-            from decodingustools_b200.callable_loci import admit_reads
-            from decodingustools_b200.callable_loci import compact_reads
-            ctx.push_reads(compact_reads(sub, admit_reads(sub, opt.pileup_max_depth, 0)))
-            g = ctx.finish_contig()
-            ok = (g.state_counts.tolist() == oc.counts and g.summed_coverage == oc.summed_coverage and g.summed_baseq == oc.summed_baseq
-                  and g.summed_mapq == oc.summed_mapq and g.quality_bases == oc.quality_bases)
-            line["parity_on_cpu_sample"] = bool(ok)
+                "sample": (f"the whole workload ({oc.summed_coverage} cells, {dt:.1f} s)" if full else
+                           f"first {sample_bp} bp of the same contig ({oc.summed_coverage} cells, {dt:.1f} s)")
+                          + f"; oracle/callable_oracle.c single-threaded like the reference, admission and BED text included; host has {os.cpu_count()} cores"}
+            obed = orun.bed()
+            if full:
+                ok = (hashlib.sha256(obed).hexdigest() == gpu_bed_sha and first.state_counts.tolist() == oc.counts
+                      and first.n_covered_bases == oc.n_covered_bases and first.summed_coverage == oc.summed_coverage
+                      and first.summed_baseq == oc.summed_baseq and first.summed_mapq == oc.summed_mapq and first.quality_bases == oc.quality_bases
+                      and oc.bins is not None and np.array_equal(first.bins, oc.bins))
+                line["parity_full"] = bool(ok)
+                line["parity_full_note"] = (f"whole contig: sha256 of the BED file written by the e2e leg ({len(obed)} bytes) == sha256 of the oracle's BED; "
+                                            "6 state counts, 5 sums and 3 x n_bins bins equal")
+            else:
+                gctx = CallableLociContext(opt, device=local_rank)
+                gctx.begin_contig(0, "chr1", sample_bp, c.ref[:sample_bp], sample_bp, max_ref_span=span)
+                gctx.push_reads(compact_reads(sub, admit_reads(sub, maxcnt, 0)))
+                g = gctx.finish_contig()
+                from decodingustools_b200.callable_loci import CallableProfiler
+                prof = CallableProfiler(None, sample_bp)
+                gb = g.bins.copy()
+                prof.add_contig("chr1", sample_bp, g.intervals, g.state_counts, gb, g.stride)
+                ok = (prof.bed_bytes() == obed and g.state_counts.tolist() == oc.counts and g.summed_coverage == oc.summed_coverage
+                      and g.summed_baseq == oc.summed_baseq and g.summed_mapq == oc.summed_mapq and g.quality_bases == oc.quality_bases
+                      and g.n_covered_bases == oc.n_covered_bases and oc.bins is not None and np.array_equal(g.bins, oc.bins))
+                line["parity_on_cpu_sample"] = bool(ok)
+                gctx.close()
+            del obed
+        if not args.no_other_configs and world == 1:
+            from decodingustools_b200 import synth
+            from decodingustools_b200.options import CallableOptions
+            ctx.close(); ctx = None                      # free the resident contig before the other configs
+            others = []
+            for tag, mk, o in (("configs[3] at reduced scale: 2000x, chrY-size/20, --max-depth 500 (cap active)",
+                                lambda: synth.synth_short("chrY", 2_800_000, 4, depth=2000.0), CallableOptions()),
+                               ("configs[3] variant: 2000x, 1 Mbp, --max-depth 4000 (no cap: true 2000x piles)",
+                                lambda: synth.synth_short("chrY", 1_000_000, 4, depth=2000.0), CallableOptions(max_depth=4000)),
+                               ("configs[4] at reduced scale: 15 kb indel-heavy long reads, 25 Mbp, 30x",
+                                lambda: synth.synth_long("chr1", 25_000_000, 5), CallableOptions())):
+                others.append(kernel_config_run(tag, mk(), o, peak))
+            line["other_configs"] = others
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
+    try:
+        os.remove(bed_path); os.rmdir(bed_dir)
+    except OSError:
+        pass
+    if nccl is not None:
+        nccl.close()
     if world > 1:
         dist.destroy_process_group()
 

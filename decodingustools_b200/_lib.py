@@ -45,14 +45,15 @@ class ContigResult(C.Structure):
                 ("stride", C.c_uint32), ("bins", C.POINTER(C.c_uint32)), ("region_start", C.c_uint32),
                 ("region_end", C.c_uint32), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("pileup_ms", C.c_float), ("fast_ms", C.c_float),
                 ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("gpu_launches", C.c_uint32), ("general_windows", C.c_uint32)]
+                ("d2h_bytes", C.c_uint64), ("gpu_launches", C.c_uint32), ("general_windows", C.c_uint32),
+                ("upload_ms", C.c_float), ("_pad", C.c_float)]
 
 
 # every symbol include/callable_loci_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "clb_abi_version", "clb_device_count", "clb_window_positions", "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream",
     "clb_begin_contig", "clb_reserve", "clb_push_reads", "clb_finish_contig", "clb_rerun_resident",
-    "clb_counters_device", "clb_refresh_counters", "clb_allreduce_nccl", "clb_debug_per_base",
+    "clb_counters_device", "clb_refresh_counters", "clb_set_nccl_allreduce", "clb_allreduce_nccl", "clb_debug_per_base",
     "clb_admit_reads", "clb_admit_reads_mt", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
     "clb_bed_writer_close", "clb_stitch_intervals", "clb_bin_geometry",
 ]
@@ -87,6 +88,7 @@ def lib() -> C.CDLL:
     L.clb_counters_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.clb_refresh_counters.argtypes = [vp, C.POINTER(ContigResult)]
     L.clb_allreduce_nccl.argtypes = [vp, vp]
+    L.clb_set_nccl_allreduce.argtypes = [vp]
     L.clb_debug_per_base.argtypes = [vp, vp, vp, vp, vp]
     L.clb_admit_reads.argtypes = [i32, u32, u64, vp, vp, vp, vp, vp]
     L.clb_admit_reads_mt.argtypes = [i32, u32, u64, vp, vp, vp, vp, u32, u32, vp, C.POINTER(u64)]

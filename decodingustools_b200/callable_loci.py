@@ -58,6 +58,7 @@ class ContigDeviceResult:
     gpu_launches: int = 0
     fast_ms: float = 0.0
     general_windows: int = 0
+    upload_ms: float = 0.0
 
 
 def _result(res: _lib.ContigResult, copy_intervals: bool = True) -> ContigDeviceResult:
@@ -72,7 +73,7 @@ def _result(res: _lib.ContigResult, copy_intervals: bool = True) -> ContigDevice
                               int(res.summed_coverage), int(res.summed_baseq), int(res.summed_mapq), int(res.quality_bases),
                               iv, bins, int(res.stride), int(res.region_start), int(res.region_end), float(res.kernel_ms),
                               float(res.h2d_ms), float(res.pileup_ms), int(res.h2d_bytes), int(res.d2h_bytes), int(res.gpu_launches),
-                              float(res.fast_ms), int(res.general_windows))
+                              float(res.fast_ms), int(res.general_windows), float(res.upload_ms))
 
 
 class CallableLociContext:
@@ -148,6 +149,17 @@ class CallableLociContext:
         self._check(self._L.clb_finish_contig(self._h, C.byref(res)))
         self._keep = self._keep[:1]
         return _result(res, copy_intervals)
+
+    def finish_contig_raw(self) -> "_lib.ContigResult":
+        """clb_finish_contig without copying anything out: the struct's pointers stay valid until the next begin_contig."""
+        res = _lib.ContigResult()
+        self._check(self._L.clb_finish_contig(self._h, C.byref(res)))
+        self._keep = self._keep[:1]
+        return res
+
+    def allreduce_nccl(self, nccl_comm: int):
+        """Sum the counter buffer over the ranks of an ncclComm_t (enqueued on the compute stream)."""
+        self._check(self._L.clb_allreduce_nccl(self._h, C.c_void_p(int(nccl_comm))))
 
     def rerun_resident(self, fetch: bool = True, copy_intervals: bool = False):
         ms = C.c_float(0)

@@ -38,7 +38,7 @@ struct clb_ctx {
     cudaStream_t s_own = nullptr, s_copy = nullptr, s_compute = nullptr;
     cudaEvent_t ev_copy = nullptr;
     std::vector<EvPair> ev_pool;        // reusable timing event pairs
-    std::vector<EvPair> ev_kernel, ev_h2d;
+    std::vector<EvPair> ev_kernel, ev_h2d, ev_upload;
     uint32_t *d_first_tab = nullptr;
     int max_ctas_per_sm = 0, n_sm = 0;
     bool force_general = false;         // CLB_FORCE_GENERAL=1: every window through the general kernel (A/B measurements, tests)
@@ -279,10 +279,11 @@ int fetch_result(clb_ctx *ctx, clb_contig_result *out) {
     ctx->h_bins.resize(3 * (size_t)ctx->n_bins);
     for (size_t i = 0; i < ctx->h_bins.size(); i++) ctx->h_bins[i] = (uint32_t)ctx->h_counters[N_STATS + i];
 
-    float kms = 0, hms = 0;
+    float kms = 0, hms = 0, ums = 0;
+    for (auto &ep : ctx->ev_upload) { float t = 0; cudaEventElapsedTime(&t, ep.a, ep.b); ums += t; ctx->ev_pool.push_back(ep); }
     for (auto &ep : ctx->ev_kernel) { float t = 0; cudaEventElapsedTime(&t, ep.a, ep.b); kms += t; ctx->ev_pool.push_back(ep); }
     for (auto &ep : ctx->ev_h2d) { float t = 0; cudaEventElapsedTime(&t, ep.a, ep.b); hms += t; ctx->ev_pool.push_back(ep); }
-    ctx->ev_kernel.clear(); ctx->ev_h2d.clear();
+    ctx->ev_kernel.clear(); ctx->ev_h2d.clear(); ctx->ev_upload.clear();
 
     if (out) {
         memset(out, 0, sizeof *out);
@@ -297,7 +298,7 @@ int fetch_result(clb_ctx *ctx, clb_contig_result *out) {
         out->n_bins = ctx->n_bins; out->stride = ctx->stride;
         out->bins = ctx->h_bins.data();
         out->region_start = ctx->region_start; out->region_end = ctx->region_end;
-        out->kernel_ms = kms; out->h2d_ms = hms;
+        out->kernel_ms = kms; out->h2d_ms = hms; out->upload_ms = ums;
         out->h2d_bytes = ctx->h2d_bytes; out->d2h_bytes = ctx->d2h_bytes;
         out->gpu_launches = ctx->launches;
         out->general_windows = ctx->h_misc[M_GEN_COUNT];
@@ -399,6 +400,7 @@ void clb_destroy(clb_ctx *ctx) {
     for (auto &ep : ctx->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     for (auto &ep : ctx->ev_kernel) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     for (auto &ep : ctx->ev_h2d) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+    for (auto &ep : ctx->ev_upload) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->s_own) cudaStreamDestroy(ctx->s_own);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
@@ -460,8 +462,12 @@ int clb_begin_contig(clb_ctx *ctx, int32_t tid, const char *name, uint32_t conti
         }
         if (contig_len) {
             const uint32_t nb = (uint32_t)(((uint64_t)contig_len + 255) / 256);
+            EvPair eu; if ((rc = get_events(ctx, eu))) return rc;
+            CU(cudaEventRecord(eu.a, ctx->s_compute));
             k_nmask_from_ascii<<<nb, 256, 0, ctx->s_compute>>>((const uint8_t *)ctx->ref_ascii.p, use, contig_len, (uint32_t *)ctx->nmask.p,
                                                               (uint32_t)n_words);
+            CU(cudaEventRecord(eu.b, ctx->s_compute));
+            ctx->ev_upload.push_back(eu);
             ctx->launches++;
         }
     } else return fail(ctx, CLB_E_INVALID, "ref_kind must be 0 (ASCII) or 1 (N-mask bits)");
@@ -531,7 +537,9 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
     CU(cudaEventRecord(ctx->ev_copy, s));
     CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copy, 0));
     EvPair ek; if ((rc = get_events(ctx, ek))) return rc;
+    EvPair eu; if ((rc = get_events(ctx, eu))) return rc;
     CU(cudaEventRecord(ek.a, ctx->s_compute));
+    CU(cudaEventRecord(eu.a, ctx->s_compute));
     const uint32_t nb = (n + 255) / 256;
     k_validate_batch<<<nb, 256, 0, ctx->s_compute>>>((const int32_t *)ctx->pos.p, (const uint32_t *)ctx->cigar_off.p,
                                                      (const uint64_t *)ctx->qual_off.p, r0, n, (uint32_t *)ctx->misc.p + M_ERR);
@@ -553,6 +561,8 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
                                                    r0, r0 + n, nullptr, (uint32_t *)ctx->misc.p + M_MAXSPAN);
         ctx->launches++;
     }
+    CU(cudaEventRecord(eu.b, ctx->s_compute));                     // upload-time helper kernels of this batch
+    ctx->ev_upload.push_back(eu);
     ctx->n_reads += n; ctx->n_cigar += b->n_cigar; ctx->n_qual += b->n_qual;
     ctx->last_pos = b->pos[n - 1];
 
@@ -630,23 +640,28 @@ int clb_refresh_counters(clb_ctx *ctx, clb_contig_result *out) {
     return fetch_result(ctx, out);
 }
 
+static void *g_nccl_allreduce = nullptr;
+
+int clb_set_nccl_allreduce(void *nccl_allreduce_fn) { g_nccl_allreduce = nccl_allreduce_fn; return CLB_OK; }
+
 int clb_allreduce_nccl(clb_ctx *ctx, void *nccl_comm) {
     if (!ctx || !ctx->in_contig || !ctx->finished) return fail(ctx, CLB_E_INVALID, "clb_allreduce_nccl needs a finished contig");
     if (!nccl_comm) return fail(ctx, CLB_E_INVALID, "nccl_comm is NULL");
-    // Resolve ncclAllReduce from the NCCL the host process already loaded (the comm belongs to it).
+    // ncclAllReduce of the NCCL build that owns the communicator: the one the host registered, else the first one visible
+    // in this process, else libnccl.so.2
     typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
-    static allreduce_fn fn = nullptr;
+    allreduce_fn fn = (allreduce_fn)g_nccl_allreduce;
     if (!fn) {
         fn = (allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
         if (!fn) { void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); if (h) fn = (allreduce_fn)dlsym(h, "ncclAllReduce"); }
         if (!fn) return fail(ctx, CLB_E_UNSUPPORTED, "ncclAllReduce not found in this process");
     }
+    CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)N_STATS + 3 * (size_t)ctx->n_bins;
-    const int ncclUint64 = 5, ncclSum = 0;       // nccl.h: ncclDataType_t / ncclRedOp_t
+    const int ncclUint64 = 5, ncclSum = 0;       // nccl.h: ncclDataType_t / ncclRedOp_t (stable since NCCL 2.0)
     const int r = fn(ctx->counters.p, ctx->counters.p, n, ncclUint64, ncclSum, nccl_comm, ctx->s_compute);
     if (r != 0) return fail(ctx, CLB_E_CUDA, "ncclAllReduce returned %d", r);
-    CU(cudaStreamSynchronize(ctx->s_compute));
-    return CLB_OK;
+    return CLB_OK;                               // asynchronous on the compute stream, like the kernels
 }
 
 /* developer hook (not part of the public header): per-window clock64 stamps of the next runs; needs a library

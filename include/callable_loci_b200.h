@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CLB_ABI_VERSION 1
+#define CLB_ABI_VERSION 2
 
 enum {
     CLB_OK = 0,
@@ -109,6 +109,9 @@ typedef struct clb_contig_result {
     uint64_t d2h_bytes;
     uint32_t gpu_launches;           /* kernels launched for this contig */
     uint32_t general_windows;        /* windows that took the general kernel (long CIGARs, deep piles, shard starts) */
+    float    upload_ms;              /* device time of the upload-time helper kernels (offset validation / rebasing, read ends and
+                                        CIGAR checkpoints of long reads, N-mask packing); part of kernel_ms, not of a resident re-run */
+    float    _pad;
 } clb_contig_result;
 
 typedef struct clb_ctx clb_ctx;
@@ -151,8 +154,11 @@ int clb_rerun_resident(clb_ctx *ctx, clb_contig_result *out, float *ms);
  * torch.distributed.all_reduce) and then re-read it with clb_refresh_counters. */
 int clb_counters_device(clb_ctx *ctx, void **dev_ptr, uint64_t *n_u64);
 int clb_refresh_counters(clb_ctx *ctx, clb_contig_result *out);
-/* Same reduction done inside the library on an ncclComm_t the host created (NULL-safe stub returns
- * CLB_E_UNSUPPORTED when the library was built without NCCL). */
+/* Same reduction done inside the library on an ncclComm_t the host created: one ncclAllReduce(ncclSum, ncclUint64) over
+ * the counter buffer, enqueued on the context's compute stream (clb_refresh_counters synchronises).  The library does
+ * not link NCCL: it calls the ncclAllReduce the host registered with clb_set_nccl_allreduce (the address of that
+ * function in the NCCL build that created the communicator), else the first one visible in the process. */
+int clb_set_nccl_allreduce(void *nccl_allreduce_fn);
 int clb_allreduce_nccl(clb_ctx *ctx, void *nccl_comm);
 
 /* Debug/parity: copy the per-base counters of [region_start, region_end) (computed by a separate

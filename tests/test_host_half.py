@@ -27,7 +27,7 @@ def states_to_intervals(states: np.ndarray) -> np.ndarray:
 
 def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
-    assert L.clb_abi_version() == 1
+    assert L.clb_abi_version() == 2
     hdr = open(os.path.join(os.path.dirname(_lib._HERE), "include", "callable_loci_b200.h")).read()
     declared = set(re.findall(r"\b(clb_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
@@ -189,3 +189,31 @@ def test_nmask_packing():
     m = n_mask_from_ascii(ref)
     for p, ch in enumerate(ref):
         assert ((int(m[p >> 5]) >> (p & 31)) & 1) == (ch in b"Nn")
+
+
+def test_bed_writer_large_contig_threads_and_file(tmp_path):
+    """More than 65536 runs: the threaded formatter, in memory and through pwrite, against plain Python formatting;
+    a small contig afterwards checks the file offset is left at the end (and quirk Q1 across the two)."""
+    rng = np.random.default_rng(77)
+    n = 150_000
+    lens = rng.integers(1, 3000, size=n)
+    ends = np.cumsum(lens); starts = ends - lens
+    st = rng.integers(0, 6, size=n).astype(np.uint8)
+    for i in range(1, n):
+        if st[i] == st[i - 1]:
+            st[i] = (st[i] + 1) % 6
+    iv = np.zeros(n, INTERVAL_DTYPE); iv["start"] = starts; iv["end"] = ends; iv["state"] = st
+    L = int(ends[-1])
+    names = ["REF_N", "CALLABLE", "NO_COVERAGE", "LOW_COVERAGE", "EXCESSIVE_COVERAGE", "POOR_MAPPING_QUALITY"]
+    want = "".join(f"chrBig\t{a}\t{b}\t{names[s]}\n" for a, b, s in zip(starts.tolist(), ends.tolist(), st.tolist()))
+    last = want.splitlines()[-1] + "\n"
+    small = np.zeros(1, INTERVAL_DTYPE); small["end"] = 7; small["state"] = 2
+    want_all = (want + last + "s\t0\t7\tNO_COVERAGE\n").encode()
+    mem = CallableProfiler(None, L)
+    mem.add_contig("chrBig", L, iv, np.zeros(6), None, 0); mem.add_contig("s", 7, small, np.zeros(6), None, 0)
+    assert mem.bed_bytes() == want_all
+    path = str(tmp_path / "big.bed")
+    f = CallableProfiler(path, L)
+    f.add_contig("chrBig", L, iv, np.zeros(6), None, 0); f.add_contig("s", 7, small, np.zeros(6), None, 0)
+    f.close()
+    assert open(path, "rb").read() == want_all
