@@ -132,3 +132,75 @@ def write_fasta(path: str, contigs: Sequence, width: int = 60):
                 f.write(line); off += len(line)
     with open(path + ".fai", "w") as f:
         f.writelines(fai)
+
+
+def read_bam(path: str):
+    """Inverse of write_bam for the test fixtures (no CG tags): returns (header_text, [(name, length)], per-tid
+    ReadColumns in file order, per-tid QNAME lists).  Records with tid < 0 are dropped."""
+    raw = open(path, "rb").read()
+    out = bytearray()
+    o = 0
+    while o < len(raw):
+        assert raw[o:o + 4] == b"\x1f\x8b\x08\x04", "not a BGZF block"
+        xlen = struct.unpack_from("<H", raw, o + 10)[0]
+        bsize = None
+        x = o + 12
+        while x < o + 12 + xlen:
+            si1, si2, slen = raw[x], raw[x + 1], struct.unpack_from("<H", raw, x + 2)[0]
+            if si1 == 66 and si2 == 67:
+                bsize = struct.unpack_from("<H", raw, x + 4)[0]
+            x += 4 + slen
+        assert bsize is not None
+        body = raw[o + 12 + xlen:o + bsize + 1 - 8]
+        out += zlib.decompress(body, -15)
+        o += bsize + 1
+    buf = bytes(out)
+    assert buf[:4] == b"BAM\1"
+    l_text = struct.unpack_from("<i", buf, 4)[0]
+    text = buf[8:8 + l_text].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", buf, p)[0]; p += 4
+    refs = []
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", buf, p)[0]; p += 4
+        name = buf[p:p + l_name - 1].decode(); p += l_name
+        refs.append((name, struct.unpack_from("<i", buf, p)[0])); p += 4
+    recs = [[] for _ in range(n_ref)]
+    names = [[] for _ in range(n_ref)]
+    while p < len(buf):
+        bs = struct.unpack_from("<i", buf, p)[0]; p += 4
+        tid, pos, l_qn, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHi", buf, p)
+        q = p + 32
+        qn = buf[q:q + l_qn - 1].decode(); q += l_qn
+        cig = np.frombuffer(buf, dtype="<u4", count=n_cig, offset=q); q += 4 * n_cig
+        q += (l_seq + 1) // 2
+        qual = np.frombuffer(buf, dtype=np.uint8, count=l_seq, offset=q)
+        p += bs
+        if tid >= 0:
+            recs[tid].append((pos, flag, mapq, cig, qual)); names[tid].append(qn)
+    cols = []
+    for tid in range(n_ref):
+        r = recs[tid]
+        ids: dict = {}
+        nid = np.array([ids.setdefault(n, len(ids)) for n in names[tid]], np.uint32)
+        cols.append(ReadColumns(
+            np.array([x[0] for x in r], np.int32), np.array([x[1] for x in r], np.uint16), np.array([x[2] for x in r], np.uint8),
+            np.concatenate([[0], np.cumsum([len(x[3]) for x in r])]).astype(np.uint32),
+            np.concatenate([x[3] for x in r]).astype(np.uint32) if r else np.zeros(0, np.uint32),
+            np.concatenate([[0], np.cumsum([len(x[4]) for x in r])]).astype(np.uint64),
+            np.concatenate([x[4] for x in r]).astype(np.uint8) if r else np.zeros(0, np.uint8), nid))
+    return text, refs, cols, names
+
+
+def read_fasta(path: str):
+    seqs, name, parts = [], None, []
+    for ln in open(path, "rb").read().split(b"\n"):
+        if ln.startswith(b">"):
+            if name is not None:
+                seqs.append((name, b"".join(parts)))
+            name, parts = ln[1:].split()[0].decode(), []
+        elif ln:
+            parts.append(ln)
+    if name is not None:
+        seqs.append((name, b"".join(parts)))
+    return seqs
