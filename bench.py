@@ -29,6 +29,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -368,13 +369,18 @@ def main():
         nonlocal mapped_only
         t0 = time.perf_counter()
         st = {}
-        keep = admit_reads(reads, maxcnt, 0, threads=0, max_ref_span=span, stats=st)
-        if mapped_only is None:
-            mapped_only = (reads.flag & 4) == 0
-        if not np.array_equal(keep, mapped_only):
-            raise SystemExit("the depth cap refused records of the 30x workload: this leg expects to stream the page-locked columns as they are")
-        t1 = time.perf_counter()
-        # only placed-unmapped records were refused: the kernels skip FLAG 0x4 themselves, no repacking needed
+        verdict = {}
+
+        def admission():
+            ta = time.perf_counter()
+            verdict["keep"] = admit_reads(reads, maxcnt, 0, threads=0, max_ref_span=span, stats=st)
+            verdict["ms"] = 1e3 * (time.perf_counter() - ta)
+        # Admission runs on host threads WHILE the column batches are being copied: the batches are pushed as they are
+        # (the kernels skip placed-unmapped records themselves); should the depth cap refuse anything else, the contig
+        # would have to be repacked and pushed again -- on 30x data it never does, and the verdict is checked before
+        # the result is used.
+        th = threading.Thread(target=admission)
+        th.start()
         ctx._check(L.clb_begin_contig(ctx._h, 0, b"chr1", c.length, ref_pinned.data_ptr(), c.length, 0, c.length, 0, c.length, span))
         ctx.reserve(reads.n, reads.n_cigar, reads.n_qual)
         for lo, hi, co, qo in batches:
@@ -382,6 +388,12 @@ def main():
                          cols["pos"].data_ptr() + 4 * lo, cols["flag"].data_ptr() + 2 * lo, cols["mapq"].data_ptr() + lo,
                          co.data_ptr(), cols["cigar"].data_ptr() + 4 * int(cig_off[lo]), qo.data_ptr(),
                          cols["qual"].data_ptr() + int(q_off[lo]))
+        th.join()
+        t1 = time.perf_counter()
+        if mapped_only is None:
+            mapped_only = (reads.flag & 4) == 0
+        if not np.array_equal(verdict["keep"], mapped_only):
+            raise SystemExit("the depth cap refused records of the 30x workload: this leg expects to stream the page-locked columns as they are")
         raw = ctx.finish_contig_raw()
         t2 = time.perf_counter()
         w = L.clb_bed_writer_open(bed_path.encode(), c.length)
@@ -393,7 +405,7 @@ def main():
         t3 = time.perf_counter()
         if rc or rc2:
             raise SystemExit(f"BED writer failed: {rc} {rc2}")
-        return raw, {"admission_ms": 1e3 * (t1 - t0), "device_pipeline_ms": 1e3 * (t2 - t1), "bed_write_ms": 1e3 * (t3 - t2),
+        return raw, {"admission_ms": verdict["ms"], "device_pipeline_ms": 1e3 * (t2 - t0), "bed_write_ms": 1e3 * (t3 - t2),
                      "total_ms": 1e3 * (t3 - t0), "admission_replayed": st.get("replayed")}
 
     raw_first, _ = e2e_pass()                # also leaves the contig resident for the HBM-resident leg
@@ -546,6 +558,7 @@ def main():
             "e2e": {"value": cells_all / (e2e_best_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_best_ms,
                     "admission_ms": round(e2e_best.get("admission_ms", float("nan")), 2),
+                    "admission_note": "host threads, concurrent with the H2D copies (inside device_pipeline_ms, not added to it)",
                     "device_pipeline_ms": round(e2e_best.get("device_pipeline_ms", float("nan")), 2),
                     "bed_write_ms": round(e2e_best.get("bed_write_ms", float("nan")), 2),
                     "admission_replayed_reads": e2e_best.get("admission_replayed"),
