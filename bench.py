@@ -484,6 +484,7 @@ def main():
     if world > 1 and not args.no_strong:
         window = int(L.clb_window_positions())
         plan = sharding.plan_regions([c.length], world, window)[rank]
+        assert len(plan) == 1, plan                        # one contig: one window-aligned region per rank
         sh = plan[0]
         lo, hi = sharding.reads_for_region(reads, sh.start, sh.end, span)
         sub = reads.slice(lo, hi)
@@ -507,16 +508,19 @@ def main():
         stitched = sharding.gather_and_stitch(part.intervals, sh.start, dst=0)
         t_strong = torch.tensor([strong_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t_strong, op=dist.ReduceOp.MAX)
-        ok = None
+        ok, detail = None, None
         if rank == 0:
-            ok = bool(np.array_equal(stitched[["start", "end", "state"]], first.intervals[["start", "end", "state"]])
-                      and np.array_equal(tot.state_counts, first.state_counts) and tot.summed_coverage == first.summed_coverage
-                      and tot.summed_baseq == first.summed_baseq and tot.summed_mapq == first.summed_mapq
-                      and tot.quality_bases == first.quality_bases and tot.n_covered_bases == first.n_covered_bases
-                      and np.array_equal(tot.bins, first.bins))
+            detail = {"intervals": bool(stitched.shape == first.intervals.shape and np.array_equal(stitched["start"], first.intervals["start"])
+                                        and np.array_equal(stitched["end"], first.intervals["end"]) and np.array_equal(stitched["state"], first.intervals["state"])),
+                      "state_counts": bool(np.array_equal(tot.state_counts, first.state_counts)),
+                      "sums": bool(tot.summed_coverage == first.summed_coverage and tot.summed_baseq == first.summed_baseq
+                                   and tot.summed_mapq == first.summed_mapq and tot.quality_bases == first.quality_bases
+                                   and tot.n_covered_bases == first.n_covered_bases),
+                      "bins": bool(np.array_equal(tot.bins, first.bins))}
+            ok = all(detail.values())
         strong = {"workload": f"the same chr1-size contig cut into {world} region shards (window-aligned), one per GPU",
                   "ms_per_step": float(t_strong[0]), "value": cells / (float(t_strong[0]) * 1e-3) / 1e9, "unit": UNIT,
-                  "shard_reads": int(sub.n), "shard_bp": int(sh.end - sh.start), "sharded_parity": ok,
+                  "shard_reads": int(sub.n), "shard_bp": int(sh.end - sh.start), "sharded_parity": ok, "sharded_parity_detail": detail,
                   "exchange": "clb_allreduce_nccl (ncclAllReduce sum of 12 counters + 3 x n_bins bins, uint64) inside the step; interval "
                               "lists gathered and stitched on rank 0 outside it"}
         ctx2.close()

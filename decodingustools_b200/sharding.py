@@ -46,7 +46,11 @@ def plan_regions(contig_lengths: Sequence[int], world_size: int, window: int) ->
                 take = max(window, take) if room > 0 else 0
                 take = min(take, length - pos)
             if take > 0:
-                per_rank[rank].append(Shard(tid, pos, pos + take))
+                mine = per_rank[rank]
+                if mine and mine[-1].tid == tid and mine[-1].end == pos:
+                    mine[-1] = Shard(tid, mine[-1].start, pos + take)     # contiguous with the rank's previous piece: one shard
+                else:
+                    mine.append(Shard(tid, pos, pos + take))
                 pos += take; used += take
             if used >= target * (rank + 1) - 1e-9 and rank < world_size - 1:
                 rank += 1

@@ -18,7 +18,8 @@ WINDOW = 2047
 
 
 def test_plan_regions_tiles_the_genome():
-    for lens, ws in ([[100_000, 50_000, 16_569], 2], [[248_956_422, 242_193_529, 16_569], 8], [[5], 4], [[0, 7000, 0], 3], [[2047 * 5], 5]):
+    for lens, ws in ([[100_000, 50_000, 16_569], 2], [[248_956_422, 242_193_529, 16_569], 8], [[5], 4], [[0, 7000, 0], 3], [[2047 * 5], 5],
+                     [[49_791_284], 2], [[248_956_422], 8], [[248_956_422], 4]):
         plan = sharding.plan_regions(lens, ws, WINDOW)
         assert len(plan) == ws
         cover = {tid: [] for tid in range(len(lens))}
@@ -33,6 +34,9 @@ def test_plan_regions_tiles_the_genome():
                 assert b == L or b % WINDOW == 0          # cuts fall on window multiples
                 pos = b
             assert pos == L
+        for shards in plan:                                   # pieces of one rank inside one contig are merged
+            for a, b in zip(shards[:-1], shards[1:]):
+                assert not (a.tid == b.tid and a.end == b.start)
         sizes = [sum(s.end - s.start for s in shards) for shards in plan]
         if sum(lens) > 50 * ws * WINDOW:
             assert max(sizes) - min(sizes) <= 2 * WINDOW + max(sizes) * 0.01
