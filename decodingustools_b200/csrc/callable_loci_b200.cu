@@ -127,7 +127,7 @@ KParams make_params(clb_ctx *c) {
     KParams P{};
     P.pos = (const int32_t *)c->pos.p; P.flag = (const uint16_t *)c->flag.p; P.mapq = (const uint8_t *)c->mapq.p;
     P.cigar_off = (const uint32_t *)c->cigar_off.p; P.cigar = (const uint32_t *)c->cigar.p;
-    P.qual_off = (const uint64_t *)c->qual_off.p; P.qual = (const uint8_t *)c->qual.p;
+    P.qual_off = (const uint64_t *)c->qual_off.p; P.qual = (const uint8_t *)c->qual.p; P.qual_bytes = c->qual.cap;
     P.read_end = c->long_mode ? (const uint32_t *)c->read_end.p : nullptr;
     P.cigar_ckpt = c->long_mode ? (const uint2 *)c->cigar_ckpt.p : nullptr;
     P.nmask = (const uint32_t *)c->nmask.p;
@@ -682,6 +682,24 @@ int clb_debug_timing(clb_ctx *ctx, long long *out, uint32_t max_windows, uint32_
     release(ctx->timing);
     return CLB_OK;
 #endif
+}
+
+/* developer hook (not part of the public header): number of out-of-bounds accesses the kernels of a -DCLB_BOUNDS_CHECK
+ * build caught (and skipped) since the last call; always 0 in production builds */
+int clb_debug_bounds(clb_ctx *ctx, uint32_t *violations, int *checked_build) {
+    if (!ctx) return CLB_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    unsigned int v = 0, zero = 0;
+    CU(cudaMemcpyFromSymbol(&v, g_clb_bounds_violations, sizeof v));
+    CU(cudaMemcpyToSymbol(g_clb_bounds_violations, &zero, sizeof zero));
+    if (violations) *violations = v;
+#ifdef CLB_BOUNDS_CHECK
+    if (checked_build) *checked_build = 1;
+#else
+    if (checked_build) *checked_build = 0;
+#endif
+    return CLB_OK;
 }
 
 int clb_debug_per_base(clb_ctx *ctx, uint32_t *raw, uint32_t *qc, uint32_t *low, uint8_t *state) {

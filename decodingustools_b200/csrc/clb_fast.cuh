@@ -84,7 +84,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-    uint4 r;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (!CLB_SMEM_OK(saddr, 16u)) return r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
     return r;
 }
@@ -150,7 +151,7 @@ __device__ __forceinline__ void stream_segment(uint32_t stage_s, uint32_t sC_s, 
 template <bool BQ_HI>
 __device__ __forceinline__ void stream_segment_global(const uint8_t *src0, uint32_t sC_s, uint32_t qs, uint32_t len, uint32_t rrel,
                                                       const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc,
-                                                      uint32_t c_first, uint32_t c_step) {
+                                                      uint32_t c_first, uint32_t c_step, const uint8_t *q_lo, const uint8_t *q_hi) {
     const uint32_t head = qs & 15u;
     const uint32_t nc = (head + len + 15u) >> 4;
     const uint4 *src = reinterpret_cast<const uint4 *>(src0 + (qs & ~15u));
@@ -159,6 +160,7 @@ __device__ __forceinline__ void stream_segment_global(const uint8_t *src0, uint3
 #pragma unroll 1
     for (uint32_t c = c_first; c < nc; c += c_step) {              // the caller spreads the chunks of a segment over c_step threads
         const uint32_t dst = dst0 + 16u * c;
+        if (!CLB_GMEM_OK(src + c, q_lo, q_hi)) continue;
         const uint4 v = ldg_stream(src + c);
         const uint32_t lo = c == 0 ? head : 0u, hi = min(16u, head + len - 16u * c);
         const uint4 ml = sMaskLo[lo], mh = sMaskHi[hi];
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             for (uint32_t x = (uint32_t)tid >> 4; x < nx; x += NT / 16) {  // 16 threads per segment, one chunk each: one L2 round trip
                 const uint2 d = sX[x];
                 stream_segment_global<BQ_HI>(P.qual + wq.x, sC_s, d.x, d.y >> 11, d.y & 0x7ffu, sMaskLo, sMaskHi, t_low, acc128,
-                                             (uint32_t)tid & 15u, 16u);
+                                             (uint32_t)tid & 15u, 16u, P.qual, P.qual + P.qual_bytes);
             }
             acc_sum += acc128 >> 7;
             __syncthreads();

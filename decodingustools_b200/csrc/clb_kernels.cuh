@@ -63,6 +63,7 @@ struct KParams {
     const uint32_t *cigar;
     const uint64_t *qual_off;
     const uint8_t  *qual;
+    uint64_t qual_bytes;           // allocated extent of qual (bounds-checked builds)
     const uint32_t *read_end;      // optional (long-read mode): pos + reference span, else nullptr
     const uint2    *cigar_ckpt;    // optional (long-read mode): (reference, query) offset of the owning read at every 32nd CIGAR op
     // contig / region
@@ -131,6 +132,7 @@ struct Win {
     uint32_t n_ent;                // entries in use = wend - wb
     uint64_t qbase;                // 16-byte aligned byte offset of the window's first candidate quality
     const uint8_t *qual;
+    uint64_t qual_bytes;
     uint32_t sA, sB;               // shared addresses of the difference arrays
     uint32_t sL;                   // deep windows only: low-MAPQ difference array (otherwise packed into the high half of sA)
     uint32_t min_bq, min_mapq, max_low_mapq;
@@ -138,21 +140,47 @@ struct Win {
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// -DCLB_BOUNDS_CHECK (developer / test builds: compute-sanitizer is not available on the GPU pool this was developed on):
+// every shared-memory atomic / vector load issued through the helpers below and every streamed quality load is checked
+// against the extent it may touch; violations are counted in g_clb_bounds_violations (read with clb_debug_bounds) and the
+// access is skipped.  Production builds compile the checks out.
+__device__ unsigned int g_clb_bounds_violations;
+#ifdef CLB_BOUNDS_CHECK
+extern __shared__ __align__(16) uint8_t clb_smem_probe[];
+__device__ __forceinline__ bool smem_ok(uint32_t saddr, uint32_t bytes) {
+    uint32_t dyn; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    const uint32_t base = smem_addr(clb_smem_probe);
+    const bool ok = saddr >= base && saddr + bytes <= base + dyn && (saddr & (bytes - 1u)) == 0u;
+    if (!ok) atomicAdd(&g_clb_bounds_violations, 1u);
+    return ok;
+}
+#define CLB_SMEM_OK(a, n) smem_ok((a), (n))
+#define CLB_GMEM_OK(p, lo, hi) (((const uint8_t *)(p) >= (const uint8_t *)(lo) && (const uint8_t *)(p) + 16 <= (const uint8_t *)(hi)) ? true : (atomicAdd(&g_clb_bounds_violations, 1u), false))
+#else
+#define CLB_SMEM_OK(a, n) true
+#define CLB_GMEM_OK(p, lo, hi) true
+#endif
+
 __device__ __forceinline__ void red_shared(uint32_t saddr, uint32_t val) {
+    if (!CLB_SMEM_OK(saddr, 4u)) return;
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(val) : "memory");
 }
 // single-lane shared atomics as plain instructions (the compiler wraps atomicAdd/atomicMax in warp-aggregation code
 // that is pure overhead when the caller has already elected one lane)
 __device__ __forceinline__ uint32_t atom_shared_add(uint32_t saddr, uint32_t val) {
-    uint32_t old;
+    uint32_t old = 0;
+    if (!CLB_SMEM_OK(saddr, 4u)) return old;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(val) : "memory");
     return old;
 }
 __device__ __forceinline__ void red_shared_max(uint32_t saddr, uint32_t val) {
+    if (!CLB_SMEM_OK(saddr, 4u)) return;
     asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(saddr), "r"(val) : "memory");
 }
 // add only when val != 0: one ISETP + one predicated ATOMS, no branch
 __device__ __forceinline__ void red_shared_nz(uint32_t saddr, uint32_t val) {
+    if (!CLB_SMEM_OK(saddr, 4u)) return;
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" :: "r"(saddr), "r"(val) : "memory");
 }
 
@@ -253,6 +281,7 @@ template <bool BQ_HI, int LAYOUT>
 __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint32_t n_owner, uint32_t S2, const uint2 *desc,
                                               const uint32_t *sRcp, const uint4 *sMaskLo, const uint4 *sMaskHi, uint32_t t_low,
                                               uint32_t &acc_sum, uint32_t f0, uint32_t stride) {
+    const uint8_t *P_qual_lo = W.qual, *P_qual_hi = W.qual + W.qual_bytes; (void)P_qual_lo; (void)P_qual_hi;
     const uint32_t total = n_owner * S2;
     const uint32_t rcp = S2 < (uint32_t)NRCP ? sRcp[S2] : 0xffffffffu / S2 + 1u;     // ceil(2^32 / S2): exact quotient for f < 2^32 / S2
     const uint8_t *qb = W.qual + W.qbase;
@@ -267,6 +296,7 @@ __device__ __forceinline__ void process_slots(const Win &W, uint32_t sLQ_s, uint
 #ifdef CLB_EXPERIMENT_NOLOAD
         const uint4 v0 = make_uint4(0x25252525u + (uint32_t)(size_t)src, 0x25250225u, 0x25252525u, 0x25252525u), v1 = v0;   // timing experiment only
 #else
+        if (!CLB_GMEM_OK(src, P_qual_lo, P_qual_hi) || !CLB_GMEM_OK(src + 1, P_qual_lo, P_qual_hi)) continue;
         const uint4 v0 = ldg_stream(src);
         const uint4 v1 = ldg_stream(src + 1);                             // may lie past the segment (buffers are padded): masked below
 #endif
@@ -433,7 +463,7 @@ __device__ __forceinline__ void pileup_classify_window(const KParams &P, const u
     Win W;
     W.wb = (long long)P.region_start + (long long)w * WREAL - 1;
     W.wend = min(W.wb + WN, (long long)P.region_end);
-    W.qual = P.qual; W.sA = smem_addr(sA); W.sB = smem_addr(sB); W.sL = WIDE ? smem_addr(sLowD) : 0u;
+    W.qual = P.qual; W.qual_bytes = P.qual_bytes; W.sA = smem_addr(sA); W.sB = smem_addr(sB); W.sL = WIDE ? smem_addr(sLowD) : 0u;
     W.min_bq = P.min_bq; W.min_mapq = P.min_mapq; W.max_low_mapq = P.max_low_mapq;
     const uint32_t n_ent = (uint32_t)(W.wend - W.wb);      // entries in use, >= 2
     W.n_ent = n_ent;
