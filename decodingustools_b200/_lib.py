@@ -52,9 +52,10 @@ class ContigResult(C.Structure):
 # every symbol include/callable_loci_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "clb_abi_version", "clb_device_count", "clb_window_positions", "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream",
-    "clb_begin_contig", "clb_reserve", "clb_push_reads", "clb_finish_contig", "clb_rerun_resident",
+    "clb_begin_contig", "clb_reserve", "clb_push_reads", "clb_finish_contig", "clb_host_alloc", "clb_host_free", "clb_wait_uploads",
+    "clb_rerun_resident",
     "clb_counters_device", "clb_refresh_counters", "clb_set_nccl_allreduce", "clb_allreduce_nccl", "clb_debug_per_base",
-    "clb_admit_reads", "clb_admit_reads_mt", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
+    "clb_admit_reads", "clb_admit_reads_mt", "clb_admitter_new", "clb_admitter_push", "clb_admitter_free", "clb_compact_reads", "clb_bed_writer_open", "clb_bed_writer_add_contig", "clb_bed_writer_buffer",
     "clb_bed_writer_close", "clb_stitch_intervals", "clb_bin_geometry",
 ]
 
@@ -91,6 +92,14 @@ def lib() -> C.CDLL:
     L.clb_set_nccl_allreduce.argtypes = [vp]
     L.clb_debug_per_base.argtypes = [vp, vp, vp, vp, vp]
     L.clb_admit_reads.argtypes = [i32, u32, u64, vp, vp, vp, vp, vp]
+    L.clb_host_alloc.restype = vp
+    L.clb_host_alloc.argtypes = [C.c_size_t]
+    L.clb_host_free.argtypes = [vp]
+    L.clb_wait_uploads.argtypes = [vp]
+    L.clb_admitter_new.restype = vp
+    L.clb_admitter_new.argtypes = [i32, u32]
+    L.clb_admitter_push.argtypes = [vp, i32, C.c_uint16, vp, u32]
+    L.clb_admitter_free.argtypes = [vp]
     L.clb_admit_reads_mt.argtypes = [i32, u32, u64, vp, vp, vp, vp, u32, u32, vp, C.POINTER(u64)]
     L.clb_compact_reads.argtypes = [C.POINTER(ReadBatch), vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(ReadBatch)]
     L.clb_bed_writer_open.restype = vp

@@ -626,6 +626,21 @@ int clb_rerun_resident(clb_ctx *ctx, clb_contig_result *out, float *ms) {
     return CLB_OK;
 }
 
+void *clb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void clb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int clb_wait_uploads(clb_ctx *ctx) {
+    if (!ctx) return CLB_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->s_copy));
+    return CLB_OK;
+}
+
 int clb_counters_device(clb_ctx *ctx, void **dev_ptr, uint64_t *n_u64) {
     if (!ctx || !ctx->in_contig) return fail(ctx, CLB_E_INVALID, "no contig");
     if (dev_ptr) *dev_ptr = ctx->counters.p;

@@ -101,6 +101,26 @@ extern "C" int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, c
     return admit_range(maxcnt, 0, n_reads, pos, flag, cigar_off, cigar, keep, ring, any, last_pos, tid == 0, -1);
 }
 
+// Streaming form for a decoder that sees one record at a time (the C++ `coverage` host packs only admitted records).
+struct clb_admitter {
+    LiveRing ring; bool any = false; long long last_pos = -1, prev = -1; bool tid0 = false; uint32_t maxcnt = 500;
+};
+extern "C" clb_admitter *clb_admitter_new(int32_t tid, uint32_t maxcnt) {
+    clb_admitter *a = new clb_admitter();
+    a->ring.init(65534); a->tid0 = tid == 0; a->maxcnt = maxcnt;      // spans beyond the ring go to its overflow heap
+    return a;
+}
+extern "C" void clb_admitter_free(clb_admitter *a) { delete a; }
+extern "C" int clb_admitter_push(clb_admitter *a, int32_t pos, uint16_t flag, const uint32_t *cigar, uint32_t n_cigar) {
+    if (!a) return CLB_E_INVALID;
+    uint8_t keep = 0;
+    const uint32_t off[2] = {0, n_cigar};
+    const int rc = admit_range(a->maxcnt, 0, 1, &pos, &flag, off, cigar, &keep, a->ring, a->any, a->last_pos, a->tid0, a->prev);
+    if (rc) return rc;
+    if (!(flag & 0x4)) a->prev = pos;
+    return keep;
+}
+
 // Same result, in parallel.  The cap can only fire at record i when at least maxcnt records start within max_span
 // before it (live <= #{j < i : pos[j] + max_span >= pos[i]}), i.e. when pos[i - maxcnt] + max_span >= pos[i]: every other
 // record is admitted whatever happened before it (zero-span rule aside).  Flagged records form runs; a run is

@@ -10,11 +10,16 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -32,78 +37,172 @@ struct BamRecordView {
     const char *qname; uint32_t l_qname; const uint32_t *cigar; const uint8_t *qual;
 };
 
-class BgzfStream {
+// N worker threads that live as long as the stream: run(fn) executes fn(t) on every worker and returns when all are done.
+class WorkerPool {
   public:
-    BgzfStream(const std::string &path, unsigned threads) : threads_(std::max(1u, threads)) {
-        fp_ = fopen(path.c_str(), "rb");
-        if (!fp_) die("Failed to open BAM file: " + path);
-        cbuf_.reserve(kChunk + (1 << 17));
+    explicit WorkerPool(unsigned n) : n_(std::max(1u, n)) {
+        for (unsigned t = 0; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
     }
-    // Continue at a compressed file offset (the upper 48 bits of a BAI virtual offset).  Reads start small and grow again,
-    // so that fetching a small contig does not inflate 64 MB of its neighbours.
-    void seek(uint64_t coffset) {
-        if (fseeko(fp_, (off_t)coffset, SEEK_SET) != 0) die("seek failed in BAM file");
-        cbuf_.clear(); eof_ = false; chunk_ = 1u << 20;
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
     }
-    ~BgzfStream() { if (fp_) fclose(fp_); }
-    // Appends the next batch of inflated bytes to out; returns false at EOF.
-    bool next(std::vector<uint8_t> &out) {
-        if (eof_ && cbuf_.empty()) return false;
-        const size_t have = cbuf_.size();
-        const size_t want = chunk_;
-        chunk_ = std::min(kChunk, chunk_ * 4);
-        cbuf_.resize(have + want);
-        const size_t got = eof_ ? 0 : fread(cbuf_.data() + have, 1, want, fp_);
-        cbuf_.resize(have + got);
-        if (got < want) eof_ = true;
-        struct Blk { size_t off, clen, ulen, uoff; };
-        std::vector<Blk> blks; size_t o = 0, utotal = 0;
-        while (o + 18 <= cbuf_.size()) {
-            const uint8_t *p = cbuf_.data() + o;
-            if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) die("not a BGZF file (bad block header)");
-            const uint32_t xlen = p[10] | (p[11] << 8);
-            if (o + 12 + xlen > cbuf_.size()) break;
-            uint32_t bsize = 0; bool found = false;
-            for (uint32_t x = 0; x + 4 <= xlen;) {
-                const uint8_t *s = p + 12 + x; const uint32_t sl = s[2] | (s[3] << 8);
-                if (s[0] == 'B' && s[1] == 'C' && sl == 2) { bsize = (s[4] | (s[5] << 8)) + 1u; found = true; }
-                x += 4 + sl;
-            }
-            if (!found) die("BGZF block without BC field");
-            if (o + bsize > cbuf_.size()) break;
-            const uint8_t *tail = p + bsize - 4;
-            const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
-            blks.push_back({o + 12 + xlen, bsize - 12 - xlen - 8, isize, utotal});
-            utotal += isize; o += bsize;
-        }
-        if (blks.empty() && !cbuf_.empty() && eof_) die("truncated BGZF file");
-        const size_t base = out.size();
-        out.resize(base + utotal);
-        std::vector<std::thread> pool; std::vector<int> err(threads_, 0);
-        for (unsigned t = 0; t < threads_; t++)
-            pool.emplace_back([&, t] {
-                for (size_t i = t; i < blks.size(); i += threads_) {
-                    if (!blks[i].ulen) continue;
-                    z_stream zs; memset(&zs, 0, sizeof zs);
-                    if (inflateInit2(&zs, -15) != Z_OK) { err[t] = 1; return; }
-                    zs.next_in = cbuf_.data() + blks[i].off; zs.avail_in = (uInt)blks[i].clen;
-                    zs.next_out = out.data() + base + blks[i].uoff; zs.avail_out = (uInt)blks[i].ulen;
-                    const int rc = inflate(&zs, Z_FINISH);
-                    inflateEnd(&zs);
-                    if (rc != Z_STREAM_END || zs.avail_out != 0) { err[t] = 1; return; }
-                }
-            });
-        for (auto &th : pool) th.join();
-        for (int e : err) if (e) die("BGZF inflate failed");
-        cbuf_.erase(cbuf_.begin(), cbuf_.begin() + (long)o);
-        return true;
+    unsigned size() const { return n_; }
+    void run(const std::function<void(unsigned)> &fn) {
+        std::unique_lock<std::mutex> g(m_);
+        fn_ = &fn; pending_ = n_; gen_++;
+        cv_.notify_all();
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
     }
 
   private:
+    void loop(unsigned t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(unsigned)> *fn;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(t);
+            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    unsigned n_; std::vector<std::thread> th_; std::mutex m_; std::condition_variable cv_, done_;
+    const std::function<void(unsigned)> *fn_ = nullptr; unsigned pending_ = 0; uint64_t gen_ = 0; bool stop_ = false;
+};
+
+// BGZF file -> inflated bytes.  A read-ahead thread reads compressed chunks, inflates their blocks on a persistent worker
+// pool and queues the results (at most kDepth chunks ahead), so the record scan never waits for zlib when the pool keeps up.
+class BgzfStream {
+  public:
+    BgzfStream(const std::string &path, unsigned threads) : pool_(std::max(1u, threads)) {
+        fp_ = fopen(path.c_str(), "rb");
+        if (!fp_) die("Failed to open BAM file: " + path);
+    }
+    ~BgzfStream() { stop_reader(); if (fp_) fclose(fp_); }
+    // Continue at a compressed file offset (the upper 48 bits of a BAI virtual offset).  Reads start small and grow again,
+    // so that fetching a small contig does not inflate 64 MB of its neighbours.
+    void seek(uint64_t coffset) {
+        stop_reader();
+        if (fseeko(fp_, (off_t)coffset, SEEK_SET) != 0) die("seek failed in BAM file");
+        chunk_ = 1u << 20;
+    }
+    // Hands out the next batch of inflated bytes: buf[kHeadroom ..) is the data, the kHeadroom bytes in front of it are
+    // free for the caller (the record scan copies the unfinished tail of the previous batch there instead of moving the
+    // batch).  Returns false at EOF.
+    static constexpr size_t kHeadroom = 4u << 20;
+    bool next(std::vector<uint8_t> &buf) {
+        if (!reader_.joinable() && !finished_) start_reader();
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [this] { return !q_.empty() || finished_; });
+        if (!error_.empty()) { const std::string e = error_; g.unlock(); die(e); }
+        if (q_.empty()) return false;
+        buf = std::move(q_.front());
+        q_.pop_front();
+        g.unlock();
+        cv_space_.notify_one();
+        return true;
+    }
+    double inflate_seconds() const { return inflate_s_; }
+
+  private:
     static constexpr size_t kChunk = 64u << 20;
+    static constexpr size_t kDepth = 2;
+    void start_reader() { stop_ = false; finished_ = false; reader_ = std::thread([this] { reader_loop(); }); }
+    void stop_reader() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_space_.notify_all();
+        if (reader_.joinable()) reader_.join();
+        q_.clear(); finished_ = false; stop_ = false; error_.clear();
+    }
+    void finish(const std::string &err) {
+        { std::lock_guard<std::mutex> g(m_); finished_ = true; if (!err.empty()) error_ = err; }
+        cv_.notify_all();
+    }
+    void reader_loop() {
+        std::vector<uint8_t> cbuf;
+        bool eof = false;
+        try {
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> g(m_);
+                    cv_space_.wait(g, [this] { return q_.size() < kDepth || stop_; });
+                    if (stop_) return;
+                }
+                if (eof && cbuf.empty()) break;
+                const size_t have = cbuf.size(), want = chunk_;
+                chunk_ = std::min(kChunk, chunk_ * 4);
+                cbuf.resize(have + want);
+                const size_t got = eof ? 0 : fread(cbuf.data() + have, 1, want, fp_);
+                cbuf.resize(have + got);
+                if (got < want) eof = true;
+                struct Blk { size_t off, clen, ulen, uoff; };
+                std::vector<Blk> blks; size_t o = 0, utotal = 0;
+                while (o + 18 <= cbuf.size()) {
+                    const uint8_t *p = cbuf.data() + o;
+                    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) die("not a BGZF file (bad block header)");
+                    const uint32_t xlen = p[10] | (p[11] << 8);
+                    if (o + 12 + xlen > cbuf.size()) break;
+                    uint32_t bsize = 0; bool found = false;
+                    for (uint32_t x = 0; x + 4 <= xlen;) {
+                        const uint8_t *s = p + 12 + x; const uint32_t sl = s[2] | (s[3] << 8);
+                        if (s[0] == 'B' && s[1] == 'C' && sl == 2) { bsize = (s[4] | (s[5] << 8)) + 1u; found = true; }
+                        x += 4 + sl;
+                    }
+                    if (!found) die("BGZF block without BC field");
+                    if (o + bsize > cbuf.size()) break;
+                    const uint8_t *tail = p + bsize - 4;
+                    const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+                    blks.push_back({o + 12 + xlen, bsize - 12 - xlen - 8, isize, utotal});
+                    utotal += isize; o += bsize;
+                }
+                if (blks.empty() && !cbuf.empty() && eof) die("truncated BGZF file");
+                std::vector<uint8_t> out(utotal ? kHeadroom + utotal : 0);
+                std::vector<int> err(pool_.size(), 0);
+                const auto t0 = std::chrono::steady_clock::now();
+                const unsigned nt = pool_.size();
+                pool_.run([&](unsigned t) {
+                    z_stream zs; memset(&zs, 0, sizeof zs);
+                    if (inflateInit2(&zs, -15) != Z_OK) { err[t] = 1; return; }
+                    for (size_t i = t; i < blks.size(); i += nt) {
+                        if (!blks[i].ulen) continue;
+                        inflateReset(&zs);
+                        zs.next_in = cbuf.data() + blks[i].off; zs.avail_in = (uInt)blks[i].clen;
+                        zs.next_out = out.data() + kHeadroom + blks[i].uoff; zs.avail_out = (uInt)blks[i].ulen;
+                        const int rc = inflate(&zs, Z_FINISH);
+                        if (rc != Z_STREAM_END || zs.avail_out != 0) { err[t] = 1; break; }
+                    }
+                    inflateEnd(&zs);
+                });
+                inflate_s_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                for (int e : err) if (e) die("BGZF inflate failed");
+                cbuf.erase(cbuf.begin(), cbuf.begin() + (long)o);
+                if (!out.empty() || (eof && cbuf.empty())) {
+                    std::lock_guard<std::mutex> g(m_);
+                    if (!out.empty()) q_.push_back(std::move(out));
+                }
+                cv_.notify_all();
+                if (eof && cbuf.empty()) break;
+            }
+            finish("");
+        } catch (const std::exception &e) {
+            finish(e.what());
+        }
+    }
+    WorkerPool pool_;
+    FILE *fp_ = nullptr;
     size_t chunk_ = kChunk;
-    FILE *fp_ = nullptr; unsigned threads_; bool eof_ = false;
-    std::vector<uint8_t> cbuf_;
+    std::thread reader_;
+    std::mutex m_; std::condition_variable cv_, cv_space_;
+    std::deque<std::vector<uint8_t>> q_;
+    bool stop_ = false, finished_ = false; std::string error_;
+    double inflate_s_ = 0;
 };
 
 class BamReader {
@@ -128,7 +227,7 @@ class BamReader {
         buf_.clear(); off_ = 0;
         const size_t skip = (size_t)(voffset & 0xffffu);
         if (skip && !need(skip)) die("BAI offset past the end of the BAM file");
-        off_ = skip;
+        off_ += skip;                                                  // need() may have moved off_ to the new batch's data start
     }
     bool next(BamRecordView &r) {
         if (!need(4)) return false;
@@ -170,11 +269,24 @@ class BamReader {
     int32_t rd32(size_t o) const { int32_t v; memcpy(&v, cur() + o, 4); return v; }
     bool need(size_t n) {
         while (buf_.size() - off_ < n) {
-            if (off_ > (32u << 20)) { buf_.erase(buf_.begin(), buf_.begin() + (long)off_); off_ = 0; }
-            if (!bz_.next(buf_)) return false;
+            std::vector<uint8_t> nb;
+            if (!bz_.next(nb)) return false;
+            const size_t tail = buf_.size() - off_;                    // unfinished bytes of the previous batch
+            if (tail <= BgzfStream::kHeadroom) {                       // the usual case: park them in the new batch's headroom
+                if (tail) memcpy(nb.data() + BgzfStream::kHeadroom - tail, buf_.data() + off_, tail);
+                buf_.swap(nb); off_ = BgzfStream::kHeadroom - tail;
+            } else {                                                   // a record larger than the headroom: join the two
+                std::vector<uint8_t> j(tail + nb.size() - BgzfStream::kHeadroom);
+                memcpy(j.data(), buf_.data() + off_, tail);
+                memcpy(j.data() + tail, nb.data() + BgzfStream::kHeadroom, nb.size() - BgzfStream::kHeadroom);
+                buf_.swap(j); off_ = 0;
+            }
         }
         return true;
     }
+  public:
+    double inflate_seconds() const { return bz_.inflate_seconds(); }
+  private:
     BgzfStream bz_; std::vector<uint8_t> buf_; size_t off_ = 0; BamHeader hdr_;
 };
 

@@ -20,7 +20,12 @@
 #include "report_writer.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -95,35 +100,97 @@ std::string reference_build(const std::string &t) {                // types.rs:1
     return "Unknown";
 }
 
-struct Columns {
-    std::vector<int32_t> pos; std::vector<uint16_t> flag; std::vector<uint8_t> mapq;
-    std::vector<uint32_t> cigar_off{0}, cigar; std::vector<uint64_t> qual_off{0}; std::vector<uint8_t> qual;
-    std::vector<uint32_t> name_off{0}; std::vector<char> names;
-    void clear() { pos.clear(); flag.clear(); mapq.clear(); cigar_off.assign(1, 0); cigar.clear(); qual_off.assign(1, 0); qual.clear(); name_off.assign(1, 0); names.clear(); }
+// One page-locked column batch of admitted records (clb_host_alloc): what clb_push_reads copies from asynchronously.
+struct PinBatch {
+    size_t n = 0, n_cigar = 0, n_qual = 0, cap_n = 0, cap_c = 0, cap_q = 0;
+    int32_t *pos = nullptr; uint16_t *flag = nullptr; uint8_t *mapq = nullptr;
+    uint32_t *cigar_off = nullptr, *cigar = nullptr; uint64_t *qual_off = nullptr; uint8_t *qual = nullptr;
+    template <class T> static void grow(T *&p, size_t used, size_t ncap) {
+        T *q = (T *)clb_host_alloc(ncap * sizeof(T));
+        if (!q) die("cannot allocate page-locked host memory");
+        if (p) { memcpy(q, p, used * sizeof(T)); clb_host_free(p); }
+        p = q;
+    }
+    void reserve(size_t rn, size_t rc, size_t rq) {
+        if (rn > cap_n) { grow(pos, n, rn); grow(flag, n, rn); grow(mapq, n, rn); grow(cigar_off, n + 1, rn + 1); grow(qual_off, n + 1, rn + 1); cap_n = rn; }
+        if (rc > cap_c) { grow(cigar, n_cigar, rc); cap_c = rc; }
+        if (rq > cap_q) { grow(qual, n_qual, rq); cap_q = rq; }
+        cigar_off[0] = 0; qual_off[0] = 0;
+    }
+    void clear() { n = n_cigar = n_qual = 0; }
+    bool fits(const BamRecordView &r) const { return n + 1 <= cap_n && n_cigar + r.n_cigar <= cap_c && n_qual + (size_t)std::max(0, r.l_seq) <= cap_q; }
     void push(const BamRecordView &r) {
-        pos.push_back(r.pos); flag.push_back(r.flag); mapq.push_back(r.mapq);
-        cigar.insert(cigar.end(), r.cigar, r.cigar + r.n_cigar); cigar_off.push_back((uint32_t)cigar.size());
-        qual.insert(qual.end(), r.qual, r.qual + std::max(0, r.l_seq)); qual_off.push_back(qual.size());
-        const uint32_t ln = r.l_qname ? r.l_qname - 1 : 0;
-        names.insert(names.end(), r.qname, r.qname + ln); name_off.push_back((uint32_t)names.size());
+        const size_t lq = (size_t)std::max(0, r.l_seq);
+        pos[n] = r.pos; flag[n] = r.flag; mapq[n] = r.mapq;
+        memcpy(cigar + n_cigar, r.cigar, 4 * (size_t)r.n_cigar); n_cigar += r.n_cigar;
+        memcpy(qual + n_qual, r.qual, lq); n_qual += lq;
+        n++;
+        cigar_off[n] = (uint32_t)n_cigar; qual_off[n] = n_qual;
+    }
+    void release() {
+        for (void *p : {(void *)pos, (void *)flag, (void *)mapq, (void *)cigar_off, (void *)cigar, (void *)qual_off, (void *)qual}) clb_host_free(p);
+        *this = PinBatch();
     }
 };
 
-uint64_t count_unique_names(const Columns &c, const std::vector<uint8_t> &keep, uint32_t contig_len) {
-    // exact distinct QNAME count among admitted records that reach >= 1 column (contig_profiler.rs:59-62)
-    std::vector<uint32_t> idx;
-    for (size_t i = 0; i < c.pos.size(); i++) {
-        if (!keep[i] || (uint32_t)c.pos[i] >= contig_len) continue;
-        uint64_t span = 0;
-        for (uint32_t k = c.cigar_off[i]; k < c.cigar_off[i + 1]; k++) { const uint32_t op = c.cigar[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c.cigar[k] >> 4; }
-        if (span) idx.push_back((uint32_t)i);
+// QNAMEs of the admitted records of one contig that reach >= 1 column, bucketed by hash: the exact distinct count
+// (contig_profiler.rs:59-62) is a sort + compare per bucket, buckets in parallel.
+struct NameStore {
+    static constexpr unsigned kBuckets = 64;
+    struct Ent { uint64_t hash; uint64_t off; uint32_t len; };
+    std::vector<char> arena;
+    std::vector<Ent> bucket[kBuckets];
+    static uint64_t fnv(const char *p, size_t n) { uint64_t h = 1469598103934665603ull; for (size_t i = 0; i < n; i++) { h ^= (uint8_t)p[i]; h *= 1099511628211ull; } return h ^ (h >> 29); }
+    void add(const char *p, uint32_t n) {
+        const uint64_t h = fnv(p, n);
+        bucket[h >> 58].push_back({h, arena.size(), n});
+        arena.insert(arena.end(), p, p + n);
     }
-    auto view = [&](uint32_t i) { return std::string_view(c.names.data() + c.name_off[i], c.name_off[i + 1] - c.name_off[i]); };
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return view(a) < view(b); });
-    uint64_t n = 0;
-    for (size_t i = 0; i < idx.size(); i++) if (i == 0 || view(idx[i]) != view(idx[i - 1])) n++;
-    return n;
-}
+    uint64_t count_unique(unsigned threads) {
+        std::vector<uint64_t> cnt(kBuckets, 0);
+        std::atomic<unsigned> next{0};
+        auto work = [&] {
+            for (;;) {
+                const unsigned b = next.fetch_add(1);
+                if (b >= kBuckets) break;
+                auto &v = bucket[b];
+                auto less = [&](const Ent &x, const Ent &y) {
+                    if (x.hash != y.hash) return x.hash < y.hash;
+                    const int c = memcmp(arena.data() + x.off, arena.data() + y.off, std::min(x.len, y.len));
+                    return c != 0 ? c < 0 : x.len < y.len;
+                };
+                std::sort(v.begin(), v.end(), less);
+                uint64_t n = 0;
+                for (size_t i = 0; i < v.size(); i++)
+                    if (i == 0 || v[i].hash != v[i - 1].hash || v[i].len != v[i - 1].len || memcmp(arena.data() + v[i].off, arena.data() + v[i - 1].off, v[i].len) != 0) n++;
+                cnt[b] = n;
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < std::max(1u, std::min(threads, kBuckets)); t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        uint64_t n = 0; for (uint64_t c : cnt) n += c;
+        return n;
+    }
+};
+
+// decoder thread -> device thread
+struct Msg { PinBatch *batch = nullptr; bool end_of_contig = false; NameStore *names = nullptr; uint64_t admitted = 0; std::string error; };
+template <class T> class Channel {
+  public:
+    void put(T v) { { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(v)); } cv_.notify_one(); }
+    T take(double *waited_s = nullptr) {
+        std::unique_lock<std::mutex> g(m_);
+        const auto t0 = std::chrono::steady_clock::now();
+        cv_.wait(g, [this] { return !q_.empty(); });
+        if (waited_s) *waited_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        T v = std::move(q_.front()); q_.pop_front();
+        return v;
+    }
+  private:
+    std::mutex m_; std::condition_variable cv_; std::deque<T> q_;
+};
 
 struct Options {
     std::string bam, reference, out_bed = "callable_regions.bed", summary = "summary.html", templates;
@@ -131,13 +198,14 @@ struct Options {
     clb_options o{4, 500, 10, 10, 20, 1, 0, 0.1};
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int device = 0;
+    bool verbose = false; std::string timing_json;
 };
 
 void usage() {
     fprintf(stderr, "Usage: decodingus-tools-b200 coverage <BAM_FILE> -r <REFERENCE> [-o callable_regions.bed] [-s summary.html] [-L contig]...\n"
                     "       [--min-depth 4] [--max-depth 500] [--min-mapping-quality 10] [--min-base-quality 20]\n"
                     "       [--min-depth-for-low-mapq 10] [--max-low-mapq 1] [--max-low-mapq-fraction 0.1] [--threads N] [--device D]\n"
-                    "       [--report-templates DIR]\n");
+                    "       [--report-templates DIR] [--verbose] [--timing-json FILE]\n");
     exit(2);
 }
 
@@ -161,6 +229,8 @@ int run(int argc, char **argv) {
         else if (a == "--threads") opt.threads = (unsigned)std::stoul(val());
         else if (a == "--device") opt.device = std::stoi(val());
         else if (a == "--report-templates") opt.templates = val();
+        else if (a == "--verbose") opt.verbose = true;
+        else if (a == "--timing-json") opt.timing_json = val();
         else if (!a.empty() && a[0] != '-' && opt.bam.empty()) opt.bam = a;
         else usage();
     }
@@ -207,42 +277,111 @@ int run(int argc, char **argv) {
     const size_t slash = opt.out_bed.find_last_of('/');
     const std::string out_dir = slash == std::string::npos ? "" : opt.out_bed.substr(0, slash + 1);
 
-    Columns cols; BamRecordView rec; bool have = indexed ? false : bam.next(rec);
+    // ------------------------------------------------------------------------------------------ the pipeline
+    // decoder thread: BGZF read-ahead + inflate pool (bam_reader.hpp) -> record scan -> htslib admission, one record at a
+    //                 time (clb_admitter_*) -> admitted records packed into page-locked column batches + QNAME store
+    // this thread   : clb_begin_contig / clb_push_reads per batch (copies overlap the kernels of earlier windows and the
+    //                 decoding of the next batch) / clb_finish_contig, BED text, plots
     const uint32_t maxcnt = opt.o.max_depth > 0 ? opt.o.max_depth : 500;
-    for (auto &kv : stats) {                                           // ascending tid (api/coverage.rs:229-235)
-        const int32_t tid = kv.first; ContigStats &st = kv.second;
-        cols.clear();
-        if (indexed) {
-            have = bai.first[(size_t)tid] != UINT64_MAX;
-            if (have) { bam.seek(bai.first[(size_t)tid]); have = bam.next(rec); }
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto secs = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
+    // batches of about a million reads for real inputs, small ones for small files (page-locking memory is not free)
+    size_t kBatchReads = 1u << 20;
+    {
+        FILE *fsz = fopen(opt.bam.c_str(), "rb");
+        if (fsz) { fseeko(fsz, 0, SEEK_END); const off_t sz = ftello(fsz); fclose(fsz); if (sz < (off_t)(256u << 20)) kBatchReads = std::max<size_t>(4096, (size_t)sz / 64); }
+    }
+    constexpr int kBatches = 3;
+    PinBatch pool[kBatches];
+    Channel<PinBatch *> free_batches;
+    Channel<Msg> ready;
+    for (auto &b : pool) { b.reserve(kBatchReads, 2 * kBatchReads, 160 * kBatchReads); free_batches.put(&b); }
+    double decode_wait_s = 0, decode_total_s = 0, admit_s = 0;
+    std::vector<int32_t> tids; std::map<int32_t, uint32_t> lens;
+    for (auto &kv : stats) { tids.push_back(kv.first); lens[kv.first] = (uint32_t)kv.second.length; }
+    std::thread decoder([&] {
+        const auto t_start = std::chrono::steady_clock::now();
+        try {
+            BamRecordView rec; bool have = indexed ? false : bam.next(rec);
+            for (const int32_t tid : tids) {                              // ascending tid (api/coverage.rs:229-235)
+                const uint32_t clen = lens.at(tid);
+                if (indexed) {
+                    have = bai.first[(size_t)tid] != UINT64_MAX;
+                    if (have) { bam.seek(bai.first[(size_t)tid]); have = bam.next(rec); }
+                }
+                while (have && (rec.tid < tid && rec.tid >= 0)) have = bam.next(rec);   // records of contigs that were not selected
+                clb_admitter *adm = clb_admitter_new(tid, maxcnt);
+                NameStore *names = new NameStore();
+                PinBatch *cur = nullptr; uint64_t admitted = 0;
+                while (have && rec.tid == tid) {
+                    const auto ta = std::chrono::steady_clock::now();
+                    const int k = clb_admitter_push(adm, rec.pos, rec.flag, rec.cigar, rec.n_cigar);
+                    admit_s += secs(ta);
+                    if (k < 0) { clb_admitter_free(adm); die("Error processing contig: records are not coordinate sorted"); }
+                    if (k == 1) {
+                        if (!cur) { cur = free_batches.take(&decode_wait_s); cur->clear(); }
+                        if (!cur->fits(rec)) {
+                            if (cur->n) { Msg m; m.batch = cur; ready.put(std::move(m)); cur = free_batches.take(&decode_wait_s); cur->clear(); }
+                            if (!cur->fits(rec)) cur->reserve(std::max<size_t>(cur->cap_n, 1), std::max<size_t>(cur->cap_c, 2 * (size_t)rec.n_cigar),
+                                                              std::max<size_t>(cur->cap_q, 2 * (size_t)std::max(0, rec.l_seq)));
+                        }
+                        cur->push(rec); admitted++;
+                        uint64_t span = 0;
+                        for (uint32_t c = 0; c < rec.n_cigar; c++) { const uint32_t op = rec.cigar[c] & 15; if ((0x18du >> op) & 1u) span += rec.cigar[c] >> 4; }
+                        if (span && (uint32_t)rec.pos < clen) names->add(rec.qname, rec.l_qname ? rec.l_qname - 1 : 0);
+                    }
+                    have = bam.next(rec);
+                }
+                clb_admitter_free(adm);
+                Msg m; m.batch = cur; m.end_of_contig = true; m.names = names; m.admitted = admitted;
+                ready.put(std::move(m));
+            }
+        } catch (const std::exception &e) {
+            Msg m; m.error = e.what(); m.end_of_contig = true; ready.put(std::move(m));
         }
-        while (have && (rec.tid < tid && rec.tid >= 0)) have = bam.next(rec);   // records of contigs that were not selected
-        while (have && rec.tid == tid) {
-            cols.push(rec);
-            have = bam.next(rec);
-        }
+        decode_total_s = secs(t_start);
+    });
+
+    double device_ms = 0, h2d_ms = 0, bed_s = 0, names_s = 0, ref_s = 0, device_wait_s = 0;
+    uint64_t total_admitted = 0, total_cells = 0;
+    std::string failure;
+    for (const int32_t tid : tids) {
+        ContigStats &st = stats[tid];
         const uint32_t clen = (uint32_t)st.length;
+        const auto tr = std::chrono::steady_clock::now();
         std::vector<uint8_t> ref;
         auto fe = fai.find(st.name);
         if (fe != fai.end()) ref = load_contig(opt.reference, fe->second);   // missing contig / short sequence reads as 'N'
-        const size_t n = cols.pos.size();
-        std::vector<uint8_t> keep(n ? n : 1, 0);
-        if (clb_admit_reads(tid, maxcnt, n, cols.pos.data(), cols.flag.data(), cols.cigar_off.data(), cols.cigar.data(), keep.data()) != 0)
-            die("Error processing contig: records are not coordinate sorted");
-        st.n_reads = count_unique_names(cols, keep, clen);
-        clb_read_batch in{n, cols.cigar.size(), cols.qual.size(), cols.pos.data(), cols.flag.data(), cols.mapq.data(),
-                          cols.cigar_off.data(), cols.cigar.data(), cols.qual_off.data(), cols.qual.data()};
-        std::vector<int32_t> p2(n ? n : 1); std::vector<uint16_t> f2(n ? n : 1); std::vector<uint8_t> m2(n ? n : 1), q2(cols.qual.size() + 1);
-        std::vector<uint32_t> co2(n + 1), c2(cols.cigar.size() + 1); std::vector<uint64_t> qo2(n + 1);
-        clb_read_batch adm{};
-        check(clb_compact_reads(&in, keep.data(), p2.data(), f2.data(), m2.data(), co2.data(), c2.data(), qo2.data(), q2.data(), &adm), "compact");
+        ref_s += secs(tr);
         check(clb_begin_contig(ctx, tid, st.name.c_str(), clen, ref.data(), ref.size(), 0, largest, 0, clen, 0), "begin");
-        if (adm.n_reads) check(clb_push_reads(ctx, &adm), "push");
+        NameStore *names = nullptr; uint64_t admitted = 0;
+        for (;;) {
+            Msg m = ready.take(&device_wait_s);
+            if (!m.error.empty()) { failure = m.error; break; }
+            if (m.batch) {
+                if (m.batch->n) {
+                    clb_read_batch rb{m.batch->n, m.batch->n_cigar, m.batch->n_qual, m.batch->pos, m.batch->flag, m.batch->mapq,
+                                      m.batch->cigar_off, m.batch->cigar, m.batch->qual_off, m.batch->qual};
+                    check(clb_push_reads(ctx, &rb), "push");
+                    check(clb_wait_uploads(ctx), "upload");                  // the batch's buffers go back to the decoder
+                }
+                free_batches.put(m.batch);
+            }
+            if (m.end_of_contig) { names = m.names; admitted = m.admitted; break; }
+        }
+        if (!failure.empty()) break;
         clb_contig_result res{};
         check(clb_finish_contig(ctx, &res), "finish");
+        device_ms += res.kernel_ms; h2d_ms += res.h2d_ms;
+        const auto tn = std::chrono::steady_clock::now();
+        st.n_reads = names ? names->count_unique(opt.threads) : 0;
+        delete names;
+        names_s += secs(tn);
         for (int s = 0; s < 6; s++) st.counts[s] = res.state_counts[s];
         st.n_covered = res.n_covered_bases; st.sum_cov = res.summed_coverage; st.sum_bq = res.summed_baseq;
         st.sum_mapq = res.summed_mapq; st.qbases = res.quality_bases;
+        total_admitted += admitted; total_cells += res.summed_coverage;
+        const auto tb = std::chrono::steady_clock::now();
         std::vector<uint32_t> bins(res.bins, res.bins + 3 * (size_t)res.n_bins);
         int has_bins = 0;
         if (clb_bed_writer_add_contig(bed, st.name.c_str(), clen, res.intervals, res.n_intervals, bins.data(), res.n_bins, res.stride, &has_bins) != 0)
@@ -254,8 +393,36 @@ int run(int argc, char **argv) {
             if (!fs) die("Error processing contig: cannot create " + path);
             fwrite(svg.data(), 1, svg.size(), fs); fclose(fs);
         }
-        fprintf(stderr, "%s: %llu admitted reads, %llu cells, %.2f ms on device\n", st.name.c_str(), (unsigned long long)adm.n_reads,
-                (unsigned long long)res.summed_coverage, res.kernel_ms);
+        bed_s += secs(tb);
+        if (opt.verbose)
+            fprintf(stderr, "%s: %llu admitted reads, %llu cells, %.2f ms on device\n", st.name.c_str(), (unsigned long long)admitted,
+                    (unsigned long long)res.summed_coverage, res.kernel_ms);
+    }
+    if (!failure.empty()) {
+        // let the decoder run dry so that it can be joined
+        std::thread drain([&] { for (;;) { Msg m = ready.take(); if (m.batch) free_batches.put(m.batch); delete m.names; if (!m.error.empty()) break; } });
+        drain.detach();
+        decoder.detach();
+        die(failure);
+    }
+    decoder.join();
+    for (auto &b : pool) b.release();
+    const double wall_s = secs(wall0);
+    fprintf(stderr, "coverage: %zu contigs, %llu admitted reads, %llu aligned bases | wall %.3f s | host decode %.3f s (BGZF inflate %.3f s on %u threads, "
+                    "admission %.3f s inline, waiting for a free batch %.3f s) | device %.3f s kernels, %.3f s H2D | reference load %.3f s | "
+                    "unique names %.3f s | BED + plots %.3f s | device thread waited %.3f s for the decoder\n",
+            tids.size(), (unsigned long long)total_admitted, (unsigned long long)total_cells, wall_s, decode_total_s - decode_wait_s,
+            bam.inflate_seconds(), opt.threads, admit_s, decode_wait_s, device_ms * 1e-3, h2d_ms * 1e-3, ref_s, names_s, bed_s, device_wait_s);
+    if (!opt.timing_json.empty()) {
+        FILE *ft = fopen(opt.timing_json.c_str(), "wb");
+        if (ft) {
+            fprintf(ft, "{\"contigs\": %zu, \"admitted_reads\": %llu, \"aligned_bases\": %llu, \"wall_s\": %.6f, \"decode_s\": %.6f, \"inflate_s\": %.6f, "
+                        "\"threads\": %u, \"admission_s\": %.6f, \"decoder_waited_for_batch_s\": %.6f, \"device_kernels_s\": %.6f, \"h2d_s\": %.6f, "
+                        "\"reference_load_s\": %.6f, \"unique_names_s\": %.6f, \"bed_and_plots_s\": %.6f, \"device_thread_waited_s\": %.6f}\n",
+                    tids.size(), (unsigned long long)total_admitted, (unsigned long long)total_cells, wall_s, decode_total_s - decode_wait_s, bam.inflate_seconds(),
+                    opt.threads, admit_s, decode_wait_s, device_ms * 1e-3, h2d_ms * 1e-3, ref_s, names_s, bed_s, device_wait_s);
+            fclose(ft);
+        }
     }
     if (clb_bed_writer_close(bed) != 0) die("failed to write " + opt.out_bed);
     clb_destroy(ctx);

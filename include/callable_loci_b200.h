@@ -144,6 +144,11 @@ int clb_reserve(clb_ctx *ctx, uint64_t n_reads, uint64_t n_cigar, uint64_t n_qua
 int clb_push_reads(clb_ctx *ctx, const clb_read_batch *batch);
 /* Finish the contig: remaining windows, interval compaction, device->host copy of the result. */
 int clb_finish_contig(clb_ctx *ctx, clb_contig_result *out);
+/* Page-locked host memory for column batches (copies from it are asynchronous and run at full PCIe speed), and a wait for
+ * every copy queued so far, after which the pushed buffers may be reused. */
+void *clb_host_alloc(size_t bytes);
+void  clb_host_free(void *p);
+int   clb_wait_uploads(clb_ctx *ctx);
 
 /* Re-run all kernels of the current (finished) contig on the data already resident in HBM and
  * refresh the result; *ms receives the device time.  This is the HBM-resident measurement path. */
@@ -178,6 +183,13 @@ int clb_admit_reads(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_
 int clb_admit_reads_mt(int32_t tid, uint32_t maxcnt, uint64_t n_reads, const int32_t *pos, const uint16_t *flag,
                        const uint32_t *cigar_off, const uint32_t *cigar, uint32_t max_ref_span, uint32_t n_threads,
                        uint8_t *keep, uint64_t *n_replayed);
+
+/* The same decision one record at a time, for a decoder that packs only admitted records: returns 1 (admitted), 0
+ * (refused or unmapped) or a negative CLB_E_* code (records out of order).  One admitter per contig. */
+typedef struct clb_admitter clb_admitter;
+clb_admitter *clb_admitter_new(int32_t tid, uint32_t maxcnt);
+int           clb_admitter_push(clb_admitter *a, int32_t pos, uint16_t flag, const uint32_t *cigar, uint32_t n_cigar);
+void          clb_admitter_free(clb_admitter *a);
 
 /* Drop the records with keep[i] == 0 and repack the columns (what the host packer does after admission).
  * Output buffers must be at least as large as the inputs; offsets are rebased to start at 0.
