@@ -204,3 +204,17 @@ def read_fasta(path: str):
     if name is not None:
         seqs.append((name, b"".join(parts)))
     return seqs
+
+
+def pack_bam_fast(path: str, name: str, length: int, reads: ReadColumns, workdir: str, threads: int = 0):
+    """A single-contig BAM through the C++ packer (decodingustools_b200/clb-pack-bam): columns are dumped as raw files,
+    records assembled and BGZF-compressed on several threads.  QNAMEs: A00123:7:HFLOWCELLX:1:1101:<contig>:<name_id>."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "decodingustools_b200", "clb-pack-bam")
+    os.makedirs(workdir, exist_ok=True)
+    nid = reads.name_id if reads.name_id is not None else np.arange(reads.n, dtype=np.uint32)
+    for fn, arr, dt in (("pos.i32", reads.pos, "<i4"), ("flag.u16", reads.flag, "<u2"), ("mapq.u8", reads.mapq, "u1"), ("cigar_off.u32", reads.cigar_off, "<u4"),
+                        ("cigar.u32", reads.cigar, "<u4"), ("qual_off.u64", reads.qual_off, "<u8"), ("qual.u8", reads.qual, "u1"), ("name_id.u32", nid, "<u4")):
+        np.ascontiguousarray(arr, dtype=dt).tofile(os.path.join(workdir, fn))
+    subprocess.check_call([exe, workdir, name, str(int(length)), path] + ([str(threads)] if threads else []))

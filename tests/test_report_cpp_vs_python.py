@@ -262,3 +262,19 @@ def test_bai_fetch_jumps_to_each_contig(shim, tmp_path, block):
     assert shim.shim_bam_fetch_tid(path.encode(), C.c_int32(0), C.byref(ps), C.byref(fv), err, C.c_size_t(256)) == -1
     (tmp_path / "i.bam.bai").write_bytes(b"BAI\1\4\0\0\0\1\0")
     assert shim.shim_bam_fetch_tid(path.encode(), C.c_int32(0), C.byref(ps), C.byref(fv), err, C.c_size_t(256)) == -2 and b"truncated BAI" in err.value
+
+
+def test_fast_bam_packer_round_trip(tmp_path):
+    """clb-pack-bam (bench infrastructure) writes what the Python reader and the C++ reader read back."""
+    from decodingustools_b200 import synth
+    from tests import bamio
+    c = synth.synth_short("chr22", 60_000, seed=77)
+    bam = str(tmp_path / "p.bam")
+    bamio.pack_bam_fast(bam, c.name, c.length, c.reads, str(tmp_path / "cols"), threads=3)
+    text, refs, cols, names = bamio.read_bam(bam)
+    assert refs == [("chr22", 60_000)] and "@PG\tID:bwa" in text
+    r, w = cols[0], c.reads
+    for k in ("pos", "flag", "mapq", "cigar_off", "cigar", "qual_off", "qual"):
+        assert np.array_equal(getattr(r, k), getattr(w, k)), k
+    assert names[0][0] == f"A00123:7:HFLOWCELLX:1:1101:chr22:{int(w.name_id[0])}"
+    assert len(set(names[0])) == len(set(w.name_id.tolist()))
