@@ -512,6 +512,11 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
     if (b->n_reads == 0) return CLB_OK;
     if (ctx->n_reads + b->n_reads >= 0xffffffffull || ctx->n_cigar + b->n_cigar >= 0xffffffffull)
         return fail(ctx, CLB_E_UNSUPPORTED, "more than 2^32 reads or CIGAR ops in one contig");
+    if (!b->pos || !b->flag || !b->mapq || !b->cigar_off || !b->qual_off || (b->n_cigar && !b->cigar) || (b->n_qual && !b->qual))
+        return fail(ctx, CLB_E_INVALID, "batch has NULL columns");
+    if (b->cigar_off[0] != 0 || b->qual_off[0] != 0) return fail(ctx, CLB_E_INPUT, "batch offsets must start at 0");
+    if (b->cigar_off[b->n_reads] != b->n_cigar || b->qual_off[b->n_reads] != b->n_qual) return fail(ctx, CLB_E_INPUT, "batch offsets do not end at n_cigar / n_qual");
+    if (b->pos[0] < 0 || (long long)b->pos[0] < ctx->last_pos) return fail(ctx, CLB_E_INPUT, "read columns are not coordinate sorted (or pos < 0)");
     CU(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = clb_reserve(ctx, ctx->n_reads + b->n_reads, ctx->n_cigar + b->n_cigar, ctx->n_qual + b->n_qual))) return rc;
@@ -530,8 +535,6 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
     CU(cudaEventRecord(ep.b, s));
     ctx->ev_h2d.push_back(ep);
     ctx->h2d_bytes += (uint64_t)n * (4 + 2 + 1 + 4 + 8) + b->n_cigar * 4 + b->n_qual;
-    if (b->cigar_off[0] != 0 || b->qual_off[0] != 0) return fail(ctx, CLB_E_INPUT, "batch offsets must start at 0");
-    if (b->cigar_off[n] != b->n_cigar || b->qual_off[n] != b->n_qual) return fail(ctx, CLB_E_INPUT, "batch offsets do not end at n_cigar / n_qual");
 
     // compute stream: wait for the copies, validate + rebase, optional read ends / max span
     CU(cudaEventRecord(ctx->ev_copy, s));

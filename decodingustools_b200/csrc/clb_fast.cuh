@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     const ulonglong2 wq = *reinterpret_cast<const ulonglong2 *>(P.win_rec + 3 * (size_t)w + 1);
     const uint32_t G = wg.x;
     if (G == 0) return;
+    if (*P.err & (ERR_UNSORTED | ERR_OFFSETS)) return;                     // k_validate_batch refused the columns: do not walk them
 #ifdef CLB_PHASE_TIMING      // developer builds only (scripts/phase_timing.py)
 #define CLB_FSTAMP(i) do { if (P.timing && threadIdx.x == 0) P.timing[(size_t)w * 8 + (i)] = clock64(); } while (0)
 #else

@@ -914,6 +914,7 @@ template <bool BQ_HI, bool DBG>
 __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_general(const KParams P) {
     __shared__ uint32_t s_ticket;
     const uint32_t n = *P.gen_count;
+    const bool refused = (*P.err & (ERR_UNSORTED | ERR_OFFSETS)) != 0;   // k_validate_batch refused the columns: take the tickets, do not walk them
     for (;;) {
         if (threadIdx.x == 0) {
             uint32_t t = atomicAdd(P.gen_taken, 1u);
@@ -923,7 +924,7 @@ __global__ void __launch_bounds__(NT, CLB_MINB) k_pileup_general(const KParams P
         __syncthreads();
         const uint32_t t = s_ticket;
         if (t == 0xffffffffu) break;
-        pileup_classify_window<BQ_HI, false, DBG>(P, P.gen_list[t]);
+        if (!refused) pileup_classify_window<BQ_HI, false, DBG>(P, P.gen_list[t]);
         __syncthreads();                                     // shared memory (and s_ticket) are reused by the next window
     }
 }

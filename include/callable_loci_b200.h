@@ -32,8 +32,9 @@ enum {
     CLB_OK = 0,
     CLB_E_INVALID = -1,     /* bad argument / call order                               */
     CLB_E_CUDA = -2,        /* CUDA runtime error (no device, OOM, launch failure)     */
-    CLB_E_INPUT = -3,       /* malformed columns: unsorted pos, offsets not monotone,
-                               read past the contig end                                */
+    CLB_E_INPUT = -3,       /* malformed columns: unsorted pos, offsets not monotone or not
+                               starting at 0 (a read that runs past the contig / region end
+                               is not an error: it is clipped there)                    */
     CLB_E_UNSUPPORTED = -4, /* a window's candidate reads span more than 4 GiB of qualities; NCCL not available */
     CLB_E_IO = -5
 };

@@ -105,6 +105,13 @@ def test_synthetic_short_reads_per_base_and_bed(ctx_default):
     assert np.array_equal(raw, oc.raw) and np.array_equal(qc, oc.qc) and np.array_equal(low, oc.low)
     assert np.array_equal(st, oc.state)
     assert results[0].summed_coverage == int(c.reads.select(admit_reads(c.reads, 500)).ref_len().sum())
+    # the per-base dump comes from the kernels' debug instantiations (<.., DBG = true>): what they left on the device must be
+    # exactly what the production instantiations produced for the same resident contig
+    dbg = ctx_default.refresh_counters()
+    prod = results[0]
+    assert np.array_equal(dbg.intervals, prod.intervals) and np.array_equal(dbg.state_counts, prod.state_counts) and np.array_equal(dbg.bins, prod.bins)
+    for k in ("n_covered_bases", "summed_coverage", "summed_baseq", "summed_mapq", "quality_bases"):
+        assert getattr(dbg, k) == getattr(prod, k), k
 
 
 def test_streamed_batches_equal_single_push(ctx_default):
@@ -309,3 +316,46 @@ def test_more_runs_than_the_first_record_buffer_holds(ctx_default):
     assert o.bed().count(b"\n") == length                                   # every run is one base long
     # the grown buffer is kept: a second contig through the same context still agrees
     assert_parity([("alt2", 0, 70_000, ref[:70_000], ReadColumns.empty())], CallableOptions(), ctx_default)
+
+
+def test_reads_past_the_contig_end_are_clipped_not_refused(ctx_default):
+    """include/callable_loci_b200.h: a read that runs past the contig end is clipped there (the reference has no guard and
+    would walk past it): the result equals the one of the same reads cut at the end by hand."""
+    ref = b"ACGT" * 25
+    long_recs = [(90, 0, 60, "20M", list(range(20, 40)), f"a{i}") for i in range(5)] + [(95, 0, 60, "3M4D10M", 30, "d")]
+    cut_recs = [(90, 0, 60, "10M", list(range(20, 30)), f"a{i}") for i in range(5)] + [(95, 0, 60, "3M2D", 30, "d")]
+    res = []
+    for recs in (long_recs, cut_recs):
+        rc = ReadColumns.from_records(recs)
+        ctx_default.begin_contig(0, "c", 100, ref, 100, max_ref_span=rc.max_ref_span())
+        ctx_default.push_reads(rc)
+        res.append(ctx_default.finish_contig())
+    a, b = res
+    assert np.array_equal(a.intervals, b.intervals) and np.array_equal(a.state_counts, b.state_counts)
+    for k in ("n_covered_bases", "summed_coverage", "summed_baseq", "summed_mapq", "quality_bases"):
+        assert getattr(a, k) == getattr(b, k), k
+    assert a.summed_coverage == 5 * 10 + 5
+
+
+def test_malformed_batches_are_refused_with_input_errors(ctx_default):
+    from decodingustools_b200._lib import ClbError
+    pos = np.array([5, 7, 9], np.int32); flag = np.zeros(3, np.uint16); mapq = np.full(3, 60, np.uint8)
+    cig = np.array([160, 160, 160], np.uint32); qoff = np.array([0, 10, 20, 30], np.uint64); qual = np.full(30, 30, np.uint8)
+    keep = [pos, flag, mapq, cig, qoff, qual]
+    p = lambda a: a.ctypes.data
+
+    def push(coff):
+        keep.append(coff)
+        ctx_default.begin_contig(0, "c", 100, b"A" * 100, 100)
+        ctx_default.push_raw(3, 3, 30, p(pos), p(flag), p(mapq), p(coff), p(cig), p(qoff), p(qual))
+    with pytest.raises(ClbError):
+        push(np.array([0, 1, 2, 2], np.uint32))              # offsets do not end at n_cigar: refused before anything is copied
+    with pytest.raises(ClbError):
+        push(np.array([1, 1, 2, 3], np.uint32))              # offsets do not start at 0
+    push(np.array([0, 2, 1, 3], np.uint32))                  # ends are right, the middle is not monotone: caught on the device, kernels do not walk it
+    with pytest.raises(ClbError):
+        ctx_default.finish_contig()
+    ctx_default.begin_contig(0, "c", 100, b"A" * 100, 100)   # the context is usable again afterwards
+    ok_off = np.array([0, 1, 2, 3], np.uint32)
+    ctx_default.push_raw(3, 3, 30, p(pos), p(flag), p(mapq), p(ok_off), p(cig), p(qoff), p(qual))
+    assert ctx_default.finish_contig().summed_coverage == 30
