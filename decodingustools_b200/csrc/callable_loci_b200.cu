@@ -456,16 +456,15 @@ int clb_begin_contig(clb_ctx *ctx, int32_t tid, const char *name, uint32_t conti
     } else if (ref_kind == 0) {
         const uint64_t use = ref ? std::min<uint64_t>(ref_len, contig_len) : 0;
         if (use) {
-            if ((rc = ensure(ctx, ctx->ref_ascii, use, false, ctx->s_compute))) return rc;
+            if ((rc = ensure(ctx, ctx->ref_ascii, use + 64, false, ctx->s_compute))) return rc;
             CU(cudaMemcpyAsync(ctx->ref_ascii.p, ref, use, cudaMemcpyHostToDevice, ctx->s_compute));
             ctx->h2d_bytes += use;
         }
         if (contig_len) {
-            const uint32_t nb = (uint32_t)(((uint64_t)contig_len + 255) / 256);
+            const uint32_t nw = (uint32_t)(((uint64_t)contig_len + 31) / 32);
             EvPair eu; if ((rc = get_events(ctx, eu))) return rc;
             CU(cudaEventRecord(eu.a, ctx->s_compute));
-            k_nmask_from_ascii<<<nb, 256, 0, ctx->s_compute>>>((const uint8_t *)ctx->ref_ascii.p, use, contig_len, (uint32_t *)ctx->nmask.p,
-                                                              (uint32_t)n_words);
+            k_nmask_from_ascii<<<(nw + 255) / 256, 256, 0, ctx->s_compute>>>((const uint8_t *)ctx->ref_ascii.p, use, contig_len, (uint32_t *)ctx->nmask.p, nw);
             CU(cudaEventRecord(eu.b, ctx->s_compute));
             ctx->ev_upload.push_back(eu);
             ctx->launches++;

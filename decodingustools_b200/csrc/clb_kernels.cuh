@@ -972,7 +972,11 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
     // the fast kernel's depth proof (pos[i] - pos[i - 254] >= max_span for every candidate), sampled: a deep pile fails it
     // at the first sample and goes to the general kernel without a wasted attempt
-    for (uint32_t i2 = r_lo + 254u; !general && i2 < r_hi; i2 += 254u) general = (long long)pos[i2 - 254u] + (long long)max_span > (long long)pos[i2];
+    if (!general) {                                      // no early exit: the loads of all samples are independent and overlap
+        bool deep = false;
+        for (uint32_t i2 = r_lo + 254u; i2 < r_hi; i2 += 254u) deep |= (long long)pos[i2 - 254u] + (long long)max_span > (long long)pos[i2];
+        general = deep;
+    }
     // Sub-batches of the fast kernel: G <= 32 reads at a time (one per lane) whose qualities fit a warp's stage.  Start
     // from the mean read length of the window and verify every sub-batch; shrink a few times before giving up.
     uint32_t G = 32;
@@ -981,11 +985,15 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
         if (total * 32u > (uint64_t)(CLB_F_WSTAGE - 16) * n_cand) G = (uint32_t)(((uint64_t)(CLB_F_WSTAGE - 16) * n_cand) / total);
         bool ok = false;
         for (int tries = 0; tries < 4 && G >= 4u && !ok; tries++) {
-            ok = true;
+            uint64_t worst = 0;                          // again without an early exit
+            uint64_t prev = qual_off[r_lo];
             for (uint32_t b = r_lo; b < r_hi; b += G) {
-                const uint64_t bytes = (qual_off[min(b + G, r_hi)] - (qual_off[b] & ~15ull) + 15ull) & ~15ull;
-                if (bytes > (uint64_t)CLB_F_WSTAGE) { ok = false; break; }
+                const uint64_t nxt = qual_off[min(b + G, r_hi)];
+                const uint64_t bytes = (nxt - (prev & ~15ull) + 15ull) & ~15ull;
+                if (bytes > worst) worst = bytes;
+                prev = nxt;
             }
+            ok = worst <= (uint64_t)CLB_F_WSTAGE;
             if (!ok) G -= max(1u, G / 8u);
         }
         if (!ok) general = true;
@@ -1047,14 +1055,32 @@ __global__ void k_rebase_batch(uint32_t *cigar_off, uint64_t *qual_off, uint32_t
     qual_off[r0 + i + 1] += qual_base;
 }
 
-// ASCII reference -> bit-packed N mask; bases past ref_len (but inside the contig) read as 'N' (mod.rs:79-80)
+// ASCII reference -> bit-packed N mask, one 32-bit word (32 bases, two 16-byte loads) per thread; bases past ref_len (but
+// inside the contig) read as 'N' (mod.rs:79-80).  ref is 256-byte aligned (cudaMalloc) and padded to a multiple of 32 bytes.
 __global__ void k_nmask_from_ascii(const uint8_t *ref, uint64_t ref_len, uint32_t contig_len, uint32_t *nmask, uint32_t n_words) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool isn = false;
-    if (p < ref_len) { const uint8_t c = ref[p]; isn = (c == 'N' || c == 'n'); }
-    else if (p < contig_len) isn = true;
-    const uint32_t word = __ballot_sync(FULL, isn);
-    if ((threadIdx.x & 31) == 0 && (p >> 5) < n_words) nmask[p >> 5] = word;
+    const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= n_words) return;
+    const uint64_t p0 = wi * 32ull;
+    uint32_t word = 0;
+    if (p0 + 32ull <= ref_len) {
+        const uint4 a = reinterpret_cast<const uint4 *>(ref + p0)[0], b = reinterpret_cast<const uint4 *>(ref + p0)[1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t x = (v[k] | 0x20202020u) ^ 0x6e6e6e6eu;          // zero byte <=> 'N' or 'n'
+            const uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // 0x80 in every zero byte
+            word |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * k);
+        }
+    } else {
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint64_t p = p0 + j;
+            bool isn = false;
+            if (p < ref_len) { const uint8_t c = ref[p]; isn = (c == 'N' || c == 'n'); }
+            else if (p < contig_len) isn = true;
+            word |= (isn ? 1u : 0u) << j;
+        }
+    }
+    nmask[wi] = word;
 }
 
 // first_tab[raw] = smallest low in [0, raw+1] with (double)low / (double)raw > fraction  (callable_profiler.rs:100-101)
