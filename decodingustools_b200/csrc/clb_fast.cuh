@@ -101,12 +101,15 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t x, uint32_t t_low) {
 // One 16-byte chunk whose bytes all belong to the segment: 6 instructions per word (LOP3, IMAD, LOP3, SHF, IDP.4A, ATOMS).
 // acc collects 128 x the sum of the passing qualities (the 0x80 flags are the dot-product weights).
 template <bool BQ_HI>
-__device__ __forceinline__ void chunk_plain(uint32_t src, uint32_t dst, uint32_t t_low, uint32_t &acc) {
-    const uint4 v = lds128(src);
+__device__ __forceinline__ void count_chunk(const uint4 v, uint32_t dst, uint32_t t_low, uint32_t &acc) {
     const uint32_t l0 = bytes_ge<BQ_HI>(v.x, t_low), l1 = bytes_ge<BQ_HI>(v.y, t_low);
     const uint32_t l2 = bytes_ge<BQ_HI>(v.z, t_low), l3 = bytes_ge<BQ_HI>(v.w, t_low);
     acc = __dp4a(v.x, l0, __dp4a(v.y, l1, __dp4a(v.z, l2, __dp4a(v.w, l3, acc))));
     red_shared(dst, l0 >> 7); red_shared(dst + 4, l1 >> 7); red_shared(dst + 8, l2 >> 7); red_shared(dst + 12, l3 >> 7);
+}
+template <bool BQ_HI>
+__device__ __forceinline__ void chunk_plain(uint32_t src, uint32_t dst, uint32_t t_low, uint32_t &acc) {
+    count_chunk<BQ_HI>(lds128(src), dst, t_low, acc);
 }
 // First / last chunk of a segment: bytes outside [lo, hi) are taken out of the pass flags.
 template <bool BQ_HI>
@@ -120,6 +123,22 @@ __device__ __forceinline__ void chunk_edge(uint32_t src, uint32_t dst, uint32_t 
     red_shared(dst, l0 >> 7); red_shared(dst + 4, l1 >> 7); red_shared(dst + 8, l2 >> 7); red_shared(dst + 12, l3 >> 7);
 }
 
+// First chunk of a segment of two or more chunks (bytes below lo are not part of it) / its last chunk (bytes from hi on are not):
+// one mask load each instead of the two of chunk_edge.
+template <bool BQ_HI>
+__device__ __forceinline__ void chunk_first(uint32_t src, uint32_t dst, uint32_t lo, const uint4 *sMaskLo, uint32_t t_low, uint32_t &acc) {
+    const uint4 v = lds128(src);
+    const uint4 ml = sMaskLo[lo];
+    const uint32_t l0 = bytes_ge<BQ_HI>(v.x, t_low) & ~ml.x, l1 = bytes_ge<BQ_HI>(v.y, t_low) & ~ml.y;
+    const uint32_t l2 = bytes_ge<BQ_HI>(v.z, t_low) & ~ml.z, l3 = bytes_ge<BQ_HI>(v.w, t_low) & ~ml.w;
+    acc = __dp4a(v.x, l0, __dp4a(v.y, l1, __dp4a(v.z, l2, __dp4a(v.w, l3, acc))));
+    red_shared(dst, l0 >> 7); red_shared(dst + 4, l1 >> 7); red_shared(dst + 8, l2 >> 7); red_shared(dst + 12, l3 >> 7);
+}
+template <bool BQ_HI>
+__device__ __forceinline__ void chunk_last(uint32_t src, uint32_t dst, uint32_t hi, const uint4 *sMaskHi, uint32_t t_low, uint32_t &acc) {
+    chunk_first<BQ_HI>(src, dst, hi, sMaskHi, t_low, acc);
+}
+
 // Stream one M-segment: qs = byte offset of its first quality inside the stage (the stage keeps the 16-byte phase of
 // the global column), len bases, rrel = window entry of the first base.  Entry e of class a lives at byte e + 16 - a of
 // array a, so a chunk whose byte 0 is entry e0 adds its four words to words (e0 >> 2) + 4 .. + 7 of array e0 & 3.
@@ -131,19 +150,18 @@ __device__ __forceinline__ void stream_segment(uint32_t stage_s, uint32_t sC_s, 
     uint32_t src = stage_s + (qs & ~15u);
     const int e0 = (int)rrel - (int)head;                                  // >= -15
     uint32_t dst = sC_s + ((uint32_t)e0 & 3u) * (uint32_t)(F_CW * 4) + (uint32_t)(((e0 >> 2) + 4) * 4);
-    chunk_edge<BQ_HI>(src, dst, head, min(16u, head + len), sMaskLo, sMaskHi, t_low, acc);
-    if (nc > 1) {
-        uint32_t n_int = nc - 2u;                                          // interior chunks: no masks, two per trip
-        src += 16; dst += 16;
+    if (nc == 1u) { chunk_edge<BQ_HI>(src, dst, head, head + len, sMaskLo, sMaskHi, t_low, acc); return; }
+    chunk_first<BQ_HI>(src, dst, head, sMaskLo, t_low, acc);
+    uint32_t n_int = nc - 2u;                                              // interior chunks: no masks
+    src += 16; dst += 16;
 #pragma unroll 1
-        for (; n_int >= 2u; n_int -= 2u) {
-            chunk_plain<BQ_HI>(src, dst, t_low, acc);
-            chunk_plain<BQ_HI>(src + 16, dst + 16, t_low, acc);
-            src += 32; dst += 32;
-        }
-        if (n_int) { chunk_plain<BQ_HI>(src, dst, t_low, acc); src += 16; dst += 16; }
-        chunk_edge<BQ_HI>(src, dst, 0u, head + len - 16u * (nc - 1u), sMaskLo, sMaskHi, t_low, acc);
+    for (; n_int >= 2u; n_int -= 2u) {
+        const uint4 v0 = lds128(src), v1 = lds128(src + 16);               // both loads in flight before the first count
+        count_chunk<BQ_HI>(v0, dst, t_low, acc); count_chunk<BQ_HI>(v1, dst + 16, t_low, acc);
+        src += 32; dst += 32;
     }
+    if (n_int) { chunk_plain<BQ_HI>(src, dst, t_low, acc); src += 16; dst += 16; }
+    chunk_last<BQ_HI>(src, dst, head + len - 16u * (nc - 1u), sMaskHi, t_low, acc);
 }
 
 // Same from global memory (the few second-and-later M-segments of a window: their qualities are in L2, one 16-byte
@@ -174,7 +192,7 @@ __device__ __forceinline__ void stream_segment_global(const uint8_t *src0, uint3
 // What a thread knows about its read of the next sub-batch: loaded one sub-batch ahead so that the DRAM round trips
 // overlap the streaming of the current one.
 struct FMeta {
-    int ps, pback; uint32_t fl, mq, c0, c1, op0, op1, op2; uint64_t q0, q1;
+    int ps, pback; uint32_t fl, mq, c0, c1, op0, op1, op2, q0, q1;   // q0, q1: relative to the window's first quality byte
 };
 // the first three CIGAR ops in one round trip (almost every short read has at most three)
 __device__ __forceinline__ void fmeta_ops(const KParams &P, FMeta &M) {
@@ -182,10 +200,10 @@ __device__ __forceinline__ void fmeta_ops(const KParams &P, FMeta &M) {
     M.op1 = M.c1 > M.c0 + 1u ? P.cigar[M.c0 + 1u] : 0xfu;
     M.op2 = M.c1 > M.c0 + 2u ? P.cigar[M.c0 + 2u] : 0xfu;
 }
-__device__ __forceinline__ void fmeta_load(const KParams &P, FMeta &M, uint32_t ic) {
+__device__ __forceinline__ void fmeta_load(const KParams &P, FMeta &M, uint32_t ic, uint64_t wqx) {
     M.fl = P.flag[ic]; M.c0 = P.cigar_off[ic]; M.c1 = P.cigar_off[ic + 1];
     M.ps = P.pos[ic]; M.mq = P.mapq[ic];
-    M.q0 = P.qual_off[ic]; M.q1 = P.qual_off[ic + 1];
+    M.q0 = (uint32_t)(P.qual_off[ic] - wqx); M.q1 = (uint32_t)(P.qual_off[ic + 1] - wqx);   // k_window_ranges checked the window's range fits 32 bits
     M.pback = P.pos[ic >= (uint32_t)F_LOOKBACK ? ic - (uint32_t)F_LOOKBACK : 0u];
 }
 
@@ -223,20 +241,20 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     const uint32_t bar = smem_addr(smem_raw + F_OFF_BAR) + 8u * (uint32_t)warp;                // and its mbarrier
     const uint32_t xcnt_s = smem_addr(const_cast<uint32_t *>(&sCtl[FC_XCNT]));
 
-    const long long wb0 = (long long)P.region_start + (long long)w * WREAL;              // position of entry 0
-    const uint32_t n_ent = (uint32_t)min((long long)WREAL, (long long)P.region_end - wb0);   // entries in use, 1 .. WREAL
+    const uint32_t wb0 = P.region_start + w * (uint32_t)WREAL;                           // position of entry 0 (BAM positions are below 2^31)
+    const uint32_t n_ent = min((uint32_t)WREAL, P.region_end - wb0);                     // entries in use, 1 .. WREAL
     const uint32_t r_lo = wr.x, r_hi = wr.y;
-    const uint32_t n_sub = (r_hi - r_lo + G - 1u) / G;                     // sub-batches of G <= 32 reads; warp v takes v, v + 8, ...
+    const uint32_t n_sub = wg.y;                                           // = ceil((r_hi - r_lo) / G), divided once by k_window_ranges;                     // sub-batches of G <= 32 reads; warp v takes v, v + 8, ...
     const uint32_t ebase = tid * PPT;
 
     // loads whose latency the setup hides: this warp's first sub-batch and the REF_N bits of phase C
     FMeta M;
     uint32_t j = (uint32_t)warp;
-    if (j < n_sub) fmeta_load(P, M, min(r_lo + j * G + (uint32_t)lane, r_hi - 1u));
+    if (j < n_sub) fmeta_load(P, M, min(r_lo + j * G + (uint32_t)lane, r_hi - 1u), wq.x);
     uint32_t nm0, nm1;
     {
-        const long long p0 = wb0 + (long long)ebase;
-        nm0 = P.nmask[(uint32_t)(p0 >> 5)]; nm1 = P.nmask[(uint32_t)(p0 >> 5) + 1];
+        const uint32_t p0 = wb0 + ebase;
+        nm0 = P.nmask[p0 >> 5]; nm1 = P.nmask[(p0 >> 5) + 1];
     }
     const uint32_t max_span = r_hi > r_lo ? *P.max_span : 0u;
     if (tid == 0 && r_hi > r_lo) l2_prefetch(P.qual, wq.x, wq.y, CLB_PREFETCH_MAX);   // the window's qualities start moving into L2
@@ -266,16 +284,14 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     // Every warp runs its own pipeline: bulk copy of its sub-batch's qualities -> CIGAR walk while the copy is in
     // flight -> next sub-batch's columns requested -> wait for the copy -> stream.  Only __syncwarp inside.
     for (; j < n_sub; j += NWARPS) {
-        if (sCtl[FC_BAIL]) break;                                          // some warp found the window is not an ordinary one
         const uint32_t rb = r_lo + j * G, n = min(G, r_hi - rb);
         __syncwarp();                                                      // every lane is done with the stage
-        const uint64_t q_first = __shfl_sync(FULL, M.q0, 0), q_last = __shfl_sync(FULL, M.q1, (int)n - 1);
-        const uint64_t sb = q_first & ~15ull;                              // stage byte 0 <-> this byte of the quality column
-        const uint64_t bytes64 = (q_last - sb + 15ull) & ~15ull;
-        const uint32_t bytes = bytes64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)bytes64;
+        const uint32_t q_first = __shfl_sync(FULL, M.q0, 0), q_last = __shfl_sync(FULL, M.q1, (int)n - 1);
+        const uint32_t sb = q_first & ~15u;                                // stage byte 0 <-> this byte of the window's qualities (wq.x is 16-byte aligned)
+        const uint32_t bytes = (q_last - sb + 15u) & ~15u;                 // q_last <= 0xfffffff0: no wrap
         const bool fits = bytes <= (uint32_t)F_WSTAGE;                     // k_window_ranges sized the sub-batches: always true
         if (!fits) sCtl[FC_BAIL] = 1;
-        if (lane == 0 && fits && bytes) { mbar_arrive_expect_tx(bar, bytes); bulk_g2s(stage_s, P.qual + sb, bytes, bar); }
+        if (lane == 0 && fits && bytes) { mbar_arrive_expect_tx(bar, bytes); bulk_g2s(stage_s, P.qual + wq.x + sb, bytes, bar); }
 
         // ---------------------------------------------------------------- phase A: one read per lane
         bool has0 = false; uint32_t s_qs = 0, s_len = 0, s_rr = 0;
@@ -286,11 +302,10 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             const uint32_t ic = rb + (uint32_t)lane;
             const bool deep = valid && ic >= (uint32_t)F_LOOKBACK && (long long)M.pback + (long long)max_span > (long long)M.ps;
             if (deep || nops > (uint32_t)F_MAXOPS) { sCtl[FC_BAIL] = 1; nops = 0; }
-            const uint64_t ql = M.q1 - M.q0;
-            const uint32_t lq = ql > 0xffffffffull ? 0xffffffffu : (uint32_t)ql;
-            const uint32_t qs_base = (uint32_t)(M.q0 - sb);                // offset of the read's first quality inside the stage
-            const uint32_t qx_base = (uint32_t)(M.q0 - wq.x);              // ... and relative to the window's first quality byte
-            const int rel = (int)((long long)M.ps - wb0);
+            const uint32_t lq = M.q1 - M.q0;
+            const uint32_t qs_base = M.q0 - sb;                            // offset of the read's first quality inside the stage
+            const uint32_t qx_base = M.q0;                                 // ... and relative to the window's first quality byte
+            const int rel = M.ps - (int)wb0;
             const uint32_t mq = M.mq, c0 = M.c0;
             const bool pass = mq >= min_mapq;
             const uint32_t kmax = __reduce_max_sync(FULL, nops);
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
         // this warp's next sub-batch: its columns are in flight while the current one is streamed
         if (j == 0) CLB_FSTAMP(2);
         const bool has_next = j + NWARPS < n_sub;
-        if (has_next) fmeta_load(P, M, min(r_lo + (j + NWARPS) * G + (uint32_t)lane, r_hi - 1u));
+        if (has_next) fmeta_load(P, M, min(r_lo + (j + NWARPS) * G + (uint32_t)lane, r_hi - 1u), wq.x);
         if (fits && bytes) { mbar_wait(bar, parity); parity ^= 1u; }       // the staged qualities have landed
         if (j == 0) CLB_FSTAMP(3);
         if (has_next) fmeta_ops(P, M);
@@ -394,7 +409,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
 #pragma unroll
         for (int k = 0; k < PPT; k++) a[k] += oa;
     }
-    const uint32_t nbits = __funnelshift_r(nm0, nm1, (uint32_t)((wb0 + (long long)ebase) & 31));
+    const uint32_t nbits = __funnelshift_r(nm0, nm1, (wb0 + ebase) & 31u);
     const uint32_t k_end = n_ent > ebase ? min((uint32_t)PPT, n_ent - ebase) : 0u;
     const uint32_t vmask = (1u << k_end) - 1u;                              // entries this thread reports
     uint32_t stp = 0;                                                       // 4 bits of state per entry
@@ -429,7 +444,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
     if (DBG && P.dbg_raw) {
 #pragma unroll
         for (int k = 0; k < PPT; k++) if ((vmask >> k) & 1u) {
-            const uint32_t o = (uint32_t)(wb0 + (long long)(ebase + k) - P.region_start);
+            const uint32_t o = wb0 + ebase + k - P.region_start;
             P.dbg_raw[o] = a[k] & 0xffffu; P.dbg_qc[o] = qcv[k]; P.dbg_low[o] = a[k] >> 16; P.dbg_state[o] = (uint8_t)((stp >> (4 * k)) & 15u);
         }
     }
@@ -493,7 +508,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             const uint32_t s = (stp >> (4 * k)) & 15u;
             const bool wsoft = w > 0 && tid == 0 && k == 0;
             if (o < P.rec_cap)
-                P.rec[o] = (unsigned long long)(uint32_t)(wb0 + (long long)(ebase + k)) | ((unsigned long long)s << 32)
+                P.rec[o] = (unsigned long long)(wb0 + ebase + k) | ((unsigned long long)s << 32)
                          | ((unsigned long long)(wsoft ? 1u : 0u) << 41);
             o++;
         }
@@ -507,7 +522,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
             uint32_t wbin0, wbin1;
             if (we1 <= nbe) { wbin0 = wbin1 = fb; }
             else if (we0 >= nbe && we1 - nbe <= P.stride) { wbin0 = wbin1 = fb + 1; }
-            else { wbin0 = (uint32_t)(wb0 + we0) / P.stride; wbin1 = (uint32_t)(wb0 + we1 - 1) / P.stride; }
+            else { wbin0 = (wb0 + we0) / P.stride; wbin1 = (wb0 + we1 - 1) / P.stride; }
             if (wbin0 == wbin1) {
                 const uint32_t s0 = __reduce_add_sync(FULL, c_call), s1 = __reduce_add_sync(FULL, c_poor), s2 = __reduce_add_sync(FULL, c_refn);
                 if (lane == 0) {
@@ -516,7 +531,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
                     if (s2) atomicAdd(&P.bins[2 * P.n_bins + wbin0], (unsigned long long)s2);
                 }
             } else if (k_end) {
-                const uint32_t tb0 = (uint32_t)(wb0 + ebase) / P.stride, tb1 = (uint32_t)(wb0 + ebase + k_end - 1) / P.stride;
+                const uint32_t tb0 = (wb0 + ebase) / P.stride, tb1 = (wb0 + ebase + k_end - 1) / P.stride;
                 if (tb0 == tb1) {
                     if (c_call) atomicAdd(&P.bins[tb0], (unsigned long long)c_call);
                     if (c_poor) atomicAdd(&P.bins[P.n_bins + tb0], (unsigned long long)c_poor);
@@ -524,7 +539,7 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
                 } else {
 #pragma unroll 1
                     for (uint32_t k = 0; k < k_end; k++) {
-                        const uint32_t bi = (uint32_t)(wb0 + ebase + k) / P.stride;
+                        const uint32_t bi = (wb0 + ebase + k) / P.stride;
                         const uint32_t s = (stp >> (4 * k)) & 15u;
                         if (s == ST_CALLABLE) atomicAdd(&P.bins[bi], 1ull);
                         else if (s == ST_POOR_MAPQ) atomicAdd(&P.bins[P.n_bins + bi], 1ull);

@@ -998,7 +998,7 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
         }
         if (!ok) general = true;
     }
-    win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, 0u, 0u, 0u);
+    win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, general ? 0u : (n_cand + G - 1u) / G, 0u, 0u);   // reads per sub-batch, sub-batches
     if (general) gen_list[atomicAdd(gen_count, 1u)] = w;
 }
 
