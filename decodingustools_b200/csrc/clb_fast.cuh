@@ -257,7 +257,6 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
         nm0 = P.nmask[p0 >> 5]; nm1 = P.nmask[(p0 >> 5) + 1];
     }
     const uint32_t max_span = r_hi > r_lo ? *P.max_span : 0u;
-    if (tid == 0 && r_hi > r_lo) l2_prefetch(P.qual, wq.x, wq.y, CLB_PREFETCH_MAX);   // the window's qualities start moving into L2
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
         for (int i = tid; i < (F_OFF_STAGE / 16); i += NT) z[i] = make_uint4(0, 0, 0, 0);
