@@ -164,7 +164,7 @@ def bind_to_gpu_numa(local_rank: int):
             bus = bus[4:]
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         if node < 0:
-            return {"numa_node": None, "note": "no NUMA information for this GPU"}
+            return share_cores(local_rank, {"numa_node": None, "note": "no NUMA information for this GPU"})
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -172,9 +172,25 @@ def bind_to_gpu_numa(local_rank: int):
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
-        return {"numa_node": node, "cores": len(cpus)}
+        return share_cores(local_rank, {"numa_node": node, "cores": len(cpus)})
     except Exception as e:      # binding is an optimisation, never a failure
-        return {"numa_node": None, "note": f"not bound: {type(e).__name__}"}
+        return share_cores(local_rank, {"numa_node": None, "note": f"not bound: {type(e).__name__}"})
+
+
+def share_cores(local_rank: int, rec: dict):
+    """Ranks that ended up on the same cores (one NUMA node for several GPUs, or no NUMA information) split them, so that the
+    host-side stages (admission, BED formatting: one thread per core of the affinity mask) do not oversubscribe the box."""
+    try:
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        cpus = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cpus) >= world:
+            per = len(cpus) // world
+            mine = cpus[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, set(mine))
+            rec["cores_of_rank"] = len(mine)
+    except Exception as e:
+        rec["share_note"] = f"cores not split: {type(e).__name__}"
+    return rec
 
 
 def make_workload(scale: float, device=None):
@@ -415,7 +431,8 @@ def main():
         batches.append((lo, hi, co, qo))
 
     ctx = CallableLociContext(opt, device=local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)            # the context's kernels, the NCCL reduction and the timing events all go on this stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     bed_dir = tempfile.mkdtemp(prefix="clb_bench_")
     bed_path = os.path.join(bed_dir, f"callable_regions.rank{rank}.bed")
@@ -500,17 +517,20 @@ def main():
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    step_ms = []
-    for _ in range(args.steps):
-        ms, _ = ctx.rerun_resident(fetch=False)
+    for _ in range(args.steps):                          # K steps queued back to back (clb_rerun_resident(ctx, NULL, NULL) only enqueues)
+        ctx.rerun_resident(fetch=False, sync=False)
         allreduce_counters()
-        step_ms.append(ms)
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
+    step_ms = []                                         # per-step device times of three more steps, outside the timed region
+    for _ in range(3):
+        ms, _ = ctx.rerun_resident(fetch=False)
+        allreduce_counters()
+        step_ms.append(ms)
     allreduce_ok = None
     if world > 1:
         summed = ctx.refresh_counters()          # the last step's counters, all-reduced: N identical replicas
@@ -533,6 +553,22 @@ def main():
         torch.cuda.synchronize()
         e2e_runs.append(tm)
     e2e_best = min(e2e_runs, key=lambda t: t["total_ms"]) if e2e_runs else {"total_ms": float("nan")}
+    # the ceiling the e2e leg runs against: a plain page-locked -> device copy of 1 GiB, all ranks at the same time
+    copy_gbs = None
+    if args.e2e_steps:
+        nb = 1 << 30
+        hsrc = torch.empty(nb, dtype=torch.uint8, pin_memory=True); hsrc.zero_()
+        ddst = torch.empty(nb, dtype=torch.uint8, device=dev)
+        ddst.copy_(hsrc, non_blocking=True); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(3):
+            ddst.copy_(hsrc, non_blocking=True)
+        c1.record(stream); torch.cuda.synchronize()
+        copy_gbs = 3 * nb / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del hsrc, ddst
     h2d_bytes, d2h_bytes, h2d_dev_ms = int(raw.h2d_bytes), int(raw.d2h_bytes), float(raw.h2d_ms)
     e2e_best_ms = e2e_best["total_ms"]
 
@@ -557,7 +593,7 @@ def main():
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(stream)
         for _ in range(args.steps):
-            ctx2.rerun_resident(fetch=False); ctx2.allreduce_nccl(nccl.comm.value)
+            ctx2.rerun_resident(fetch=False, sync=False); ctx2.allreduce_nccl(nccl.comm.value)
         s1.record(stream)
         torch.cuda.synchronize(); dist.barrier()
         strong_ms = s0.elapsed_time(s1) / args.steps
@@ -583,16 +619,18 @@ def main():
         ctx2.close()
 
     # ---------------- max over ranks
-    t_total = torch.tensor([total_ms, e2e_best_ms, float(cells), h2d_bytes / max(h2d_dev_ms, 1e-9) / 1e6], dtype=torch.float64, device=dev)
+    t_total = torch.tensor([total_ms, e2e_best_ms, float(cells), h2d_bytes / max(h2d_dev_ms, 1e-9) / 1e6, copy_gbs or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t_total.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t_total.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         tmin = t_total.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         total_ms, e2e_best_ms, cells_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
         h2d_rank_gbs = {"min": float(tmin[3]), "max": float(tmax[3])}
+        copy_rank_gbs = {"min": float(tmin[4]), "max": float(tmax[4])}
     else:
         cells_all = float(cells)
         h2d_rank_gbs = {"min": float(t_total[3]), "max": float(t_total[3])}
+        copy_rank_gbs = {"min": float(t_total[4]), "max": float(t_total[4])}
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -624,6 +662,9 @@ def main():
                     "bed_write_ms": round(e2e_best.get("bed_write_ms", float("nan")), 2),
                     "admission_replayed_reads": e2e_best.get("admission_replayed"),
                     "h2d_device_ms": round(h2d_dev_ms, 2), "h2d_GBps_per_rank": h2d_rank_gbs,
+                    "h2d_ceiling_GBps_per_rank": copy_rank_gbs,
+                    "h2d_ceiling_note": "plain cudaMemcpyAsync of 1 GiB page-locked -> device, all ranks at the same time: what the host's PCIe / memory "
+                                        "system gives each rank; the e2e leg's copies run at h2d_GBps_per_rank",
                     "bed_bytes": os.path.getsize(bed_path),
                     "note": "per contig: clb_admit_reads_mt (htslib depth cap) + clb_begin_contig + clb_push_reads batches from page-locked host "
                             "columns + clb_finish_contig (D2H) + clb_bed_writer_* to a real file; the device part is PCIe-bound"},

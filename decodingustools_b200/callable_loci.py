@@ -161,7 +161,10 @@ class CallableLociContext:
         """Sum the counter buffer over the ranks of an ncclComm_t (enqueued on the compute stream)."""
         self._check(self._L.clb_allreduce_nccl(self._h, C.c_void_p(int(nccl_comm))))
 
-    def rerun_resident(self, fetch: bool = True, copy_intervals: bool = False):
+    def rerun_resident(self, fetch: bool = True, copy_intervals: bool = False, sync: bool = True):
+        if not fetch and not sync:                       # enqueue only (clb_rerun_resident(ctx, NULL, NULL))
+            self._check(self._L.clb_rerun_resident(self._h, None, None))
+            return None, None
         ms = C.c_float(0)
         if fetch:
             res = _lib.ContigResult()

@@ -307,7 +307,7 @@ int fetch_result(clb_ctx *ctx, clb_contig_result *out) {
 }
 
 // all kernels of the resident contig, from scratch (used for re-runs and record-buffer growth)
-int run_all_resident(clb_ctx *ctx, float *ms, float *pileup_ms = nullptr, float *fast_ms = nullptr) {
+int run_all_resident(clb_ctx *ctx, float *ms, float *pileup_ms = nullptr, float *fast_ms = nullptr, bool sync = true) {
     int rc;
     EvPair ep, ek, ef;
     if ((rc = get_events(ctx, ep))) return rc;
@@ -319,6 +319,10 @@ int run_all_resident(clb_ctx *ctx, float *ms, float *pileup_ms = nullptr, float 
     if ((rc = launch_windows(ctx, 0, ctx->n_windows, &ek, &ef))) return rc;
     if ((rc = launch_compaction(ctx))) return rc;
     CU(cudaEventRecord(ep.b, ctx->s_compute));
+    if (!sync) {                                             // enqueue only: the caller waits (clb_refresh_counters / the next synchronous call)
+        ctx->ev_pool.push_back(ep); ctx->ev_pool.push_back(ek); ctx->ev_pool.push_back(ef);
+        return CLB_OK;
+    }
     CU(cudaStreamSynchronize(ctx->s_compute));
     float t = 0;
     CU(cudaEventElapsedTime(&t, ep.a, ep.b));
@@ -615,7 +619,7 @@ int clb_rerun_resident(clb_ctx *ctx, clb_contig_result *out, float *ms) {
     int rc;
     const uint32_t l0 = ctx->launches;
     float t = 0, tp = 0, tf = 0;
-    if ((rc = run_all_resident(ctx, &t, &tp, &tf))) return rc;
+    if ((rc = run_all_resident(ctx, &t, &tp, &tf, out != nullptr || ms != nullptr))) return rc;
     if (ms) *ms = t;
     if (out) {
         rc = fetch_result(ctx, out);

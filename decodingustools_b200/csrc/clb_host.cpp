@@ -20,6 +20,19 @@
 
 #include <unistd.h>
 
+#include <sched.h>
+// host threads this process may use: the cores of its affinity mask (a rank bound to its GPU's cores gets its share,
+// not the whole machine), capped at 16
+static uint32_t clb_host_threads() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    unsigned n = 0;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = (unsigned)CPU_COUNT(&set);
+    if (n == 0) n = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(16u, n));
+}
+
+
 static const char *kStateName[6] = {"REF_N", "CALLABLE", "NO_COVERAGE", "LOW_COVERAGE", "EXCESSIVE_COVERAGE", "POOR_MAPPING_QUALITY"};
 
 namespace {
@@ -135,7 +148,7 @@ extern "C" int clb_admit_reads_mt(int32_t tid, uint32_t maxcnt, uint64_t n_reads
     if (maxcnt == 0) { if (n_replayed) *n_replayed = n_reads; return clb_admit_reads(tid, maxcnt, n_reads, pos, flag, cigar_off, cigar, keep); }
     // automatic thread count: all cores (at most 16) but at least 16384 records per thread; an explicit count is
     // honoured down to 64 records per thread
-    if (n_threads == 0) n_threads = (uint32_t)std::min<uint64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), (n_reads + 16383) / 16384);
+    if (n_threads == 0) n_threads = (uint32_t)std::min<uint64_t>(clb_host_threads(), (n_reads + 16383) / 16384);
     n_threads = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_threads, (n_reads + 63) / 64));
     const uint64_t chunk = (n_reads + n_threads - 1) / n_threads;
     auto parallel = [&](auto &&fn) {
@@ -385,7 +398,7 @@ extern "C" int clb_bed_writer_add_contig(clb_bed_writer *w, const char *name, ui
     } else {
         // large contigs: format on several threads, each into its own reusable buffer, then copy / pwrite the parts to
         // their final offsets in parallel (BED text of a 30x human chromosome is ~100 MB)
-        const uint32_t nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const uint32_t nt = clb_host_threads();
         const bool dbg_t = getenv("CLB_ADMIT_DEBUG") != nullptr;
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double t0 = now();

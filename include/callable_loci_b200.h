@@ -152,7 +152,9 @@ void  clb_host_free(void *p);
 int   clb_wait_uploads(clb_ctx *ctx);
 
 /* Re-run all kernels of the current (finished) contig on the data already resident in HBM and
- * refresh the result; *ms receives the device time.  This is the HBM-resident measurement path. */
+ * refresh the result; *ms receives the device time.  This is the HBM-resident measurement path.
+ * With out == NULL and ms == NULL the kernels are only ENQUEUED on the context's compute stream (no host
+ * synchronisation): steps, and a clb_allreduce_nccl after each, can be queued back to back and waited for once. */
 int clb_rerun_resident(clb_ctx *ctx, clb_contig_result *out, float *ms);
 
 /* Multi-GPU: the additive part of the result (11 counters + 3*n_bins bins, all uint64) lives in one
