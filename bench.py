@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the contig (1.0 = chr1, 248.96 Mbp)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-pipelined", type=int, default=6, help="contigs of the pipelined e2e leg (0: report the single-contig time as e2e)")
     ap.add_argument("--cpu-sample-mbp", type=float, default=48.0, help="oracle sample of the bounded CPU legs (Mbp of the contig)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU oracle leg (cpu_baseline, parity)")
     ap.add_argument("--no-parity-full", action="store_true", help="check parity on the bounded sample only, not on the whole contig")
@@ -438,8 +439,9 @@ def main():
     bed_path = os.path.join(bed_dir, f"callable_regions.rank{rank}.bed")
     mapped_only = None
 
-    def e2e_pass():
-        """What `coverage` does for one contig, from host buffers to the BED file."""
+    def e2e_pass(defer_bed=False):
+        """What `coverage` does for one contig, from host buffers to the BED file.  defer_bed: return the BED step as a job
+        for a writer thread (it gets its own copy of the interval list) instead of running it here."""
         nonlocal mapped_only
         t0 = time.perf_counter()
         st = {}
@@ -470,17 +472,27 @@ def main():
             raise SystemExit("the depth cap refused records of the 30x workload: this leg expects to stream the page-locked columns as they are")
         raw = ctx.finish_contig_raw()
         t2 = time.perf_counter()
-        w = L.clb_bed_writer_open(bed_path.encode(), c.length)
         bins = np.ctypeslib.as_array(raw.bins, shape=(3 * int(raw.n_bins),)).copy()
-        has = C.c_int(0)
-        rc = L.clb_bed_writer_add_contig(w, b"chr1", c.length, raw.intervals, raw.n_intervals, bins.ctypes.data_as(C.c_void_p),
-                                         raw.n_bins, raw.stride, C.byref(has))
-        rc2 = L.clb_bed_writer_close(w)
-        t3 = time.perf_counter()
-        if rc or rc2:
-            raise SystemExit(f"BED writer failed: {rc} {rc2}")
-        return raw, {"admission_ms": verdict["ms"], "device_pipeline_ms": 1e3 * (t2 - t0), "bed_write_ms": 1e3 * (t3 - t2),
-                     "total_ms": 1e3 * (t3 - t0), "admission_replayed": st.get("replayed")}
+        n_iv, n_bins, stride = int(raw.n_intervals), int(raw.n_bins), int(raw.stride)
+
+        def write_bed(iv_ptr, keep=None):
+            tb = time.perf_counter()
+            w = L.clb_bed_writer_open(bed_path.encode(), c.length)
+            has = C.c_int(0)
+            rc = L.clb_bed_writer_add_contig(w, b"chr1", c.length, iv_ptr, n_iv, bins.ctypes.data_as(C.c_void_p), n_bins, stride, C.byref(has))
+            rc2 = L.clb_bed_writer_close(w)
+            if rc or rc2:
+                raise SystemExit(f"BED writer failed: {rc} {rc2}")
+            return 1e3 * (time.perf_counter() - tb)
+        tm = {"admission_ms": verdict["ms"], "device_pipeline_ms": 1e3 * (t2 - t0), "admission_replayed": st.get("replayed")}
+        if defer_bed:
+            # the context's interval buffer is reused by the next contig: the writer thread works on its own copy
+            iv_copy = np.ctypeslib.as_array(C.cast(raw.intervals, C.POINTER(C.c_uint8)), shape=(n_iv * INTERVAL_DTYPE.itemsize,)).copy()
+            tm["total_ms"] = 1e3 * (time.perf_counter() - t0)
+            return raw, tm, (lambda: write_bed(iv_copy.ctypes.data_as(C.c_void_p), iv_copy))
+        tm["bed_write_ms"] = write_bed(raw.intervals)
+        tm["total_ms"] = 1e3 * (time.perf_counter() - t0)
+        return raw, tm
 
     raw_first, _ = e2e_pass()                # also leaves the contig resident for the HBM-resident leg
     first = _result(raw_first, True)
@@ -553,6 +565,28 @@ def main():
         torch.cuda.synchronize()
         e2e_runs.append(tm)
     e2e_best = min(e2e_runs, key=lambda t: t["total_ms"]) if e2e_runs else {"total_ms": float("nan")}
+    # The same steps as consecutive contigs of a genome: contig i's BED text is formatted and written by a writer thread while
+    # contig i + 1 is admitted and uploaded (what a host does between two process_single_contig calls).  Wall time of the
+    # whole sequence, last BED file included, divided by the number of contigs.
+    e2e_pipe_ms, pipe_n = float("nan"), max(0, args.e2e_pipelined)
+    if pipe_n:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tp0 = time.perf_counter()
+        writer, bed_ms = None, []
+        for i in range(pipe_n):
+            raw, _, job = e2e_pass(defer_bed=True)
+            allreduce_counters()
+            if writer is not None:
+                writer.join()
+            writer = threading.Thread(target=lambda j=job: bed_ms.append(j()))
+            writer.start()
+        writer.join()
+        torch.cuda.synchronize()
+        e2e_pipe_ms = 1e3 * (time.perf_counter() - tp0) / pipe_n
+        if hashlib.sha256(open(bed_path, "rb").read()).hexdigest() != gpu_bed_sha:
+            raise SystemExit("the BED file of the pipelined e2e leg differs from the first pass")
     # the ceiling the e2e leg runs against: a plain page-locked -> device copy of 1 GiB, all ranks at the same time
     copy_gbs = None
     if args.e2e_steps:
@@ -570,7 +604,8 @@ def main():
         copy_gbs = 3 * nb / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del hsrc, ddst
     h2d_bytes, d2h_bytes, h2d_dev_ms = int(raw.h2d_bytes), int(raw.d2h_bytes), float(raw.h2d_ms)
-    e2e_best_ms = e2e_best["total_ms"]
+    e2e_single_ms = e2e_best["total_ms"]
+    e2e_best_ms = e2e_pipe_ms if pipe_n else e2e_single_ms
 
     # ---------------- strong scaling: ONE chr1 cut into N region shards (halo reads, all-reduce, stitching, parity)
     strong = None
@@ -619,12 +654,13 @@ def main():
         ctx2.close()
 
     # ---------------- max over ranks
-    t_total = torch.tensor([total_ms, e2e_best_ms, float(cells), h2d_bytes / max(h2d_dev_ms, 1e-9) / 1e6, copy_gbs or 0.0], dtype=torch.float64, device=dev)
+    t_total = torch.tensor([total_ms, e2e_best_ms, float(cells), h2d_bytes / max(h2d_dev_ms, 1e-9) / 1e6, copy_gbs or 0.0, e2e_single_ms],
+                           dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t_total.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t_total.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         tmin = t_total.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-        total_ms, e2e_best_ms, cells_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        total_ms, e2e_best_ms, cells_all, e2e_single_ms = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[5])
         h2d_rank_gbs = {"min": float(tmin[3]), "max": float(tmax[3])}
         copy_rank_gbs = {"min": float(tmin[4]), "max": float(tmax[4])}
     else:
@@ -656,6 +692,12 @@ def main():
                                    "outside the resident step `value` times (inside `e2e`)",
             "e2e": {"value": cells_all / (e2e_best_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_best_ms,
+                    "steps": pipe_n if pipe_n else args.e2e_steps,
+                    "pipelining": (f"{pipe_n} contigs back to back; contig i's BED text is written by a writer thread while contig i + 1 is admitted and "
+                                   "uploaded; wall time of the whole sequence (last BED file included) / contigs" if pipe_n else "none: best single contig"),
+                    "single_contig_ms": e2e_single_ms,
+                    "single_contig_note": "one contig alone, nothing overlapped across contigs: admission || upload, kernels, D2H, then the BED file "
+                                          "(best of --e2e-steps passes); the three *_ms fields below are this pass",
                     "admission_ms": round(e2e_best.get("admission_ms", float("nan")), 2),
                     "admission_note": "host threads, concurrent with the H2D copies (inside device_pipeline_ms, not added to it)",
                     "device_pipeline_ms": round(e2e_best.get("device_pipeline_ms", float("nan")), 2),
