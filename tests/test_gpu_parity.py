@@ -359,3 +359,15 @@ def test_malformed_batches_are_refused_with_input_errors(ctx_default):
     ok_off = np.array([0, 1, 2, 3], np.uint32)
     ctx_default.push_raw(3, 3, 30, p(pos), p(flag), p(mapq), p(ok_off), p(cig), p(qoff), p(qual))
     assert ctx_default.finish_contig().summed_coverage == 30
+
+
+@pytest.mark.parametrize("min_depth,max_depth,min_dflm,frac", [
+    (0, 0, 0, 0.0), (4, 127, 10, 0.1), (127, 128, 128, 0.0), (128, 253, 120, 0.5), (160, 254, 300, 0.1), (200, 255, 0, -0.5),
+    (255, 1000, 5, 1.0), (256, 100, 129, 0.25), (1000, 1, 200, 0.0), (100, 140, 100, 0.02)])
+def test_byte_wide_thresholds_on_a_deep_short_read_pile(min_depth, max_depth, min_dflm, frac):
+    """Depths of 100-200 with thresholds on both sides of 128 / 255: every depth of a fast window is held in byte-wide counters."""
+    c = synth.synth_short("chr21", 40_000, seed=77, depth=150.0)
+    opt = CallableOptions(min_depth=min_depth, max_depth=max_depth, min_depth_for_low_mapq=min_dflm, max_low_mapq_fraction=frac,
+                          max_low_mapq=3)
+    o, results = assert_parity([(c.name, 0, c.length, c.ref, c.reads)], opt)
+    assert results[0].general_windows < 5          # the pile stays below 255: the fast kernel takes (nearly) all windows
