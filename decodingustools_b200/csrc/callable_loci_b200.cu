@@ -164,7 +164,7 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     if (w1 <= w0) return CLB_OK;
     const uint32_t n = w1 - w0;
     const bool all_general = ctx->force_general || ctx->long_mode;
-    k_window_ranges<<<(n + 127) / 128, 128, 0, ctx->s_compute>>>(
+    k_window_ranges<<<(n + 7) / 8, 256, 0, ctx->s_compute>>>(                    // one warp per window
         (const int32_t *)ctx->pos.p, (uint32_t)ctx->n_reads, ctx->region_start, ctx->region_end,
         (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p, (const uint32_t *)ctx->cigar_off.p, ctx->stride,
         (uint4 *)ctx->win_rec.p, all_general ? 1u : 0u, (uint32_t *)ctx->gen_list.p, (uint32_t *)ctx->misc.p + M_GEN_COUNT);

@@ -943,39 +943,52 @@ __global__ void __launch_bounds__(NT, 1) k_pileup_classify_deep(const KParams P)
 // ---------------------------------------------------------------------------------------------
 // Small helper kernels
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t n, long long key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if ((long long)pos[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
+// Warp-cooperative lower bound: 32 probes per round trip (the range shrinks 33-fold per step: 6 dependent loads for 48 M
+// reads instead of 26).
+__device__ __forceinline__ uint32_t lower_bound_pos_warp(const int32_t *pos, uint32_t n, long long key, int lane) {
+    uint32_t lo = 0, hi = n;                             // the answer lies in [lo, hi]
+    while (hi - lo > 32u) {
+        const uint32_t idx = lo + (uint32_t)(((unsigned long long)(hi - lo) * (unsigned)(lane + 1)) / 33u);   // lo < idx < hi, increasing with the lane
+        const uint32_t below = __ballot_sync(FULL, (long long)pos[idx] < key);                                // monotone: a run of ones, then zeros
+        const int c = __popc(below);
+        const uint32_t lo_n = c ? __shfl_sync(FULL, idx, c - 1) + 1u : lo;
+        const uint32_t hi_n = c < 32 ? __shfl_sync(FULL, idx, c & 31) : hi;
+        lo = lo_n; hi = hi_n;
+    }
+    const uint32_t i = lo + (uint32_t)lane;
+    return lo + (uint32_t)__popc(__ballot_sync(FULL, i < hi && (long long)pos[i] < key));
 }
 
 // candidate read range of every window: reads with pos < window end and pos + max_span > halo position; and the
 // window's class: shard-first windows (they need the state of the base before the shard), windows of long-read contigs
 // and windows whose candidate count or CIGAR density cannot be an ordinary short-read pile go straight to the general queue.
+// One warp per window: the searches probe 32 positions per step and the two verification loops are spread over the lanes
+// (one thread per window spent 80 us of a 2.8 ms chr1 step in ~70 dependent round trips).
 __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t region_start, uint32_t region_end,
                                 const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w,
                                 const uint64_t *qual_off, const uint32_t *cigar_off, uint32_t stride, uint4 *win_rec,
                                 uint32_t force_general, uint32_t *gen_list, uint32_t *gen_count) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_w) return;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_w) return;                                // whole warps leave together
     const uint32_t max_span = *max_span_ptr;
     const uint32_t w = w_first + i;
     const long long wb = (long long)region_start + (long long)w * WREAL - 1;
     const long long wend = min(wb + WN, (long long)region_end);
-    const uint32_t r_lo = lower_bound_pos(pos, n_reads, wb - (long long)max_span + 1), r_hi = lower_bound_pos(pos, n_reads, wend);
+    const uint32_t r_lo = lower_bound_pos_warp(pos, n_reads, wb - (long long)max_span + 1, lane);
+    const uint32_t r_hi = lower_bound_pos_warp(pos, n_reads, wend, lane);
     const uint32_t first_bin = stride ? (uint32_t)(wb + 1) / stride : 0u;
     const uint64_t q_lo = qual_off[r_lo] & ~15ull, q_hi = qual_off[r_hi];
-    win_rec[3 * (size_t)w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
-    *reinterpret_cast<ulonglong2 *>(win_rec + 3 * (size_t)w + 1) = make_ulonglong2(q_lo, q_hi);
     const uint32_t n_cand = r_hi - r_lo;
     bool general = force_general != 0 || (w == 0 && region_start != 0) || n_cand > 16384u || q_hi - q_lo > 0xfffffff0ull;
     if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
     // the fast kernel's depth proof (pos[i] - pos[i - 254] >= max_span for every candidate), sampled: a deep pile fails it
     // at the first sample and goes to the general kernel without a wasted attempt
-    if (!general) {                                      // no early exit: the loads of all samples are independent and overlap
+    if (!general) {
         bool deep = false;
-        for (uint32_t i2 = r_lo + 254u; i2 < r_hi; i2 += 254u) deep |= (long long)pos[i2 - 254u] + (long long)max_span > (long long)pos[i2];
-        general = deep;
+        for (uint32_t i2 = r_lo + 254u * (uint32_t)(lane + 1); i2 < r_hi; i2 += 254u * 32u)
+            deep |= (long long)pos[i2 - 254u] + (long long)max_span > (long long)pos[i2];
+        general = __any_sync(FULL, deep);
     }
     // Sub-batches of the fast kernel: G <= 32 reads at a time (one per lane) whose qualities fit a warp's stage.  Start
     // from the mean read length of the window and verify every sub-batch; shrink a few times before giving up.
@@ -985,21 +998,22 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
         if (total * 32u > (uint64_t)(CLB_F_WSTAGE - 16) * n_cand) G = (uint32_t)(((uint64_t)(CLB_F_WSTAGE - 16) * n_cand) / total);
         bool ok = false;
         for (int tries = 0; tries < 4 && G >= 4u && !ok; tries++) {
-            uint64_t worst = 0;                          // again without an early exit
-            uint64_t prev = qual_off[r_lo];
-            for (uint32_t b = r_lo; b < r_hi; b += G) {
-                const uint64_t nxt = qual_off[min(b + G, r_hi)];
-                const uint64_t bytes = (nxt - (prev & ~15ull) + 15ull) & ~15ull;
-                if (bytes > worst) worst = bytes;
-                prev = nxt;
+            uint32_t worst = 0;                          // staged bytes of the largest sub-batch, saturated
+            for (uint32_t b = r_lo + (uint32_t)lane * G; b < r_hi; b += 32u * G) {
+                const uint64_t bytes = (qual_off[min(b + G, r_hi)] - (qual_off[b] & ~15ull) + 15ull) & ~15ull;
+                worst = max(worst, (uint32_t)min(bytes, (uint64_t)0xffffffffu));
             }
-            ok = worst <= (uint64_t)CLB_F_WSTAGE;
+            ok = __reduce_max_sync(FULL, worst) <= (uint32_t)CLB_F_WSTAGE;
             if (!ok) G -= max(1u, G / 8u);
         }
         if (!ok) general = true;
     }
-    win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, general ? 0u : (n_cand + G - 1u) / G, 0u, 0u);   // reads per sub-batch, sub-batches
-    if (general) gen_list[atomicAdd(gen_count, 1u)] = w;
+    if (lane == 0) {
+        win_rec[3 * (size_t)w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
+        *reinterpret_cast<ulonglong2 *>(win_rec + 3 * (size_t)w + 1) = make_ulonglong2(q_lo, q_hi);
+        win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, general ? 0u : (n_cand + G - 1u) / G, 0u, 0u);   // reads per sub-batch, sub-batches
+        if (general) gen_list[atomicAdd(gen_count, 1u)] = w;
+    }
 }
 
 // pos + reference span of every read, and the maximum span (long-read mode / max_ref_span == 0)
