@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(NT, CLB_F_MINB) k_pileup_fast(const KParams P)
         nm0 = P.nmask[p0 >> 5]; nm1 = P.nmask[(p0 >> 5) + 1];
     }
     const uint32_t max_span = r_hi > r_lo ? *P.max_span : 0u;
+    // the CIGAR ops are the last hop of the window's first dependent chain (table record -> columns -> ops): start them towards L2 now
+    if (tid == 0 && wg.w > wg.z) l2_prefetch(P.cigar, 4ull * wg.z, 4ull * wg.w, 64u << 10);
     {
         uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
         for (int i = tid; i < (F_OFF_STAGE / 16); i += NT) z[i] = make_uint4(0, 0, 0, 0);

@@ -79,7 +79,7 @@ struct KParams {
     // windows
     // per window, three 16-byte words (k_window_ranges): [0] candidate reads [x, y), first histogram bin z, window entry w where the
     // next bin starts; [1] quality bytes [lo (16-byte aligned), hi) of the candidate reads as two u64; [2] x = reads per warp
-    // sub-batch of k_pileup_fast (0: general-path window)
+    // sub-batch of k_pileup_fast (0: general-path window), y = sub-batches, [z, w) = CIGAR ops of the candidate reads
     const uint4 *win_rec;
     uint32_t win_first;
     // outputs
@@ -981,7 +981,8 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     const uint64_t q_lo = qual_off[r_lo] & ~15ull, q_hi = qual_off[r_hi];
     const uint32_t n_cand = r_hi - r_lo;
     bool general = force_general != 0 || (w == 0 && region_start != 0) || n_cand > 16384u || q_hi - q_lo > 0xfffffff0ull;
-    if (!general && n_cand) general = (cigar_off[r_hi] - cigar_off[r_lo]) > 8u * n_cand + 64u;
+    const uint32_t c_lo = cigar_off[r_lo], c_hi = cigar_off[r_hi];
+    if (!general && n_cand) general = (c_hi - c_lo) > 8u * n_cand + 64u;
     // the fast kernel's depth proof (pos[i] - pos[i - 254] >= max_span for every candidate), sampled: a deep pile fails it
     // at the first sample and goes to the general kernel without a wasted attempt
     if (!general) {
@@ -1011,7 +1012,7 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     if (lane == 0) {
         win_rec[3 * (size_t)w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
         *reinterpret_cast<ulonglong2 *>(win_rec + 3 * (size_t)w + 1) = make_ulonglong2(q_lo, q_hi);
-        win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, general ? 0u : (n_cand + G - 1u) / G, 0u, 0u);   // reads per sub-batch, sub-batches
+        win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, general ? 0u : (n_cand + G - 1u) / G, c_lo, c_hi);   // reads per sub-batch, sub-batches, CIGAR op range
         if (general) gen_list[atomicAdd(gen_count, 1u)] = w;
     }
 }
