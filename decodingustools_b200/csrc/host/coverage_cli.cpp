@@ -206,14 +206,14 @@ struct Options {
     clb_options o{4, 500, 10, 10, 20, 1, 0, 0.1};
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     int device = 0;
-    bool verbose = false; std::string timing_json;
+    bool verbose = false, progress = false; std::string timing_json;
 };
 
 void usage() {
     fprintf(stderr, "Usage: decodingus-tools-b200 coverage <BAM_FILE> -r <REFERENCE> [-o callable_regions.bed] [-s summary.html] [-L contig]...\n"
                     "       [--min-depth 4] [--max-depth 500] [--min-mapping-quality 10] [--min-base-quality 20]\n"
                     "       [--min-depth-for-low-mapq 10] [--max-low-mapq 1] [--max-low-mapq-fraction 0.1] [--threads N] [--device D]\n"
-                    "       [--report-templates DIR] [--verbose] [--timing-json FILE]\n");
+                    "       [--report-templates DIR] [--verbose] [--progress] [--timing-json FILE]\n");
     exit(2);
 }
 
@@ -238,6 +238,7 @@ int run(int argc, char **argv) {
         else if (a == "--device") opt.device = std::stoi(val());
         else if (a == "--report-templates") opt.templates = val();
         else if (a == "--verbose") opt.verbose = true;
+        else if (a == "--progress") opt.progress = true;
         else if (a == "--timing-json") opt.timing_json = val();
         else if (!a.empty() && a[0] != '-' && opt.bam.empty()) opt.bam = a;
         else usage();
@@ -356,6 +357,13 @@ int run(int argc, char **argv) {
     double device_ms = 0, h2d_ms = 0, bed_s = 0, names_s = 0, ref_s = 0, device_wait_s = 0;
     uint64_t total_admitted = 0, total_cells = 0;
     std::string failure;
+    // --progress: the reference API's ProgressEvent stream (api/mod.rs:12-18, emitted by CoverageAnalyzer::analyze at
+    // api/coverage.rs:40-48), one serde-style JSON object per line on stderr; Progress counts finished contigs
+    auto progress = [&](const char *kind, const std::string &extra) {
+        if (opt.progress) fprintf(stderr, "{\"%s\":{\"task\":\"Coverage Analysis\"%s}}\n", kind, extra.c_str());
+    };
+    progress("Started", "");
+    size_t contigs_done = 0;
     for (const int32_t tid : tids) {
         ContigStats &st = stats[tid];
         const uint32_t clen = (uint32_t)st.length;
@@ -408,12 +416,14 @@ int run(int argc, char **argv) {
         if (opt.verbose)
             fprintf(stderr, "%s: %llu admitted reads, %llu cells, %.2f ms on device\n", st.name.c_str(), (unsigned long long)admitted,
                     (unsigned long long)res.summed_coverage, res.kernel_ms);
+        progress("Progress", ",\"current\":" + std::to_string(++contigs_done) + ",\"total\":" + std::to_string(tids.size()));
     }
     if (!failure.empty()) {
         // let the decoder run dry so that it can be joined
         std::thread drain([&] { for (;;) { Msg m = ready.take(); if (m.batch) free_batches.put(m.batch); delete m.names; if (!m.error.empty()) break; } });
         drain.detach();
         decoder.detach();
+        progress("Error", ",\"error\":\"" + failure + "\"");
         die(failure);
     }
     decoder.join();
@@ -503,6 +513,7 @@ int run(int argc, char **argv) {
     FILE *fh = fopen(opt.summary.c_str(), "wb");
     if (!fh) die("cannot create " + opt.summary);
     fwrite(html.data(), 1, html.size(), fh); fclose(fh);
+    progress("Completed", "");
     return 0;
 }
 

@@ -120,3 +120,18 @@ def test_cli_report_outputs_match_the_python_mirror(tmp_path):
         html = (tmp_path / "summary.html").read_text()
         assert html == report.render_html_report(js["export"], header_html=head, footer_html=foot, plot_exists=lambda q: (tmp_path / q).exists())
         assert html.count("<figure") == sum(oc.bins is not None for oc in o.contigs) > 0
+
+
+def test_cli_progress_events_follow_the_reference_api(tmp_path):
+    """--progress: the reference API's ProgressEvent stream (api/mod.rs:12-18) as serde-style JSON lines on stderr."""
+    cs = [synth.synth_short("chr1", 30_000, seed=51), synth.synth_short("chr2", 20_000, seed=52)]
+    bam = str(tmp_path / "in.bam"); fa = str(tmp_path / "ref.fa")
+    bamio.write_bam(bam, [(c.name, c.length, c.reads) for c in cs], index=False, block=0xFF00)
+    bamio.write_fasta(fa, [(c.name, c.ref) for c in cs])
+    p = subprocess.run([CLI, "coverage", bam, "-r", fa, "-o", str(tmp_path / "out.bed"), "--progress"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    events = [json.loads(line) for line in p.stderr.splitlines() if line.startswith("{")]
+    task = {"task": "Coverage Analysis"}
+    assert events[0] == {"Started": task} and events[-1] == {"Completed": task}
+    assert events[1:-1] == [{"Progress": {**task, "current": i + 1, "total": 2}} for i in range(2)]
