@@ -552,13 +552,17 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
     k_rebase_batch<<<nb, 256, 0, ctx->s_compute>>>((uint32_t *)ctx->cigar_off.p, (uint64_t *)ctx->qual_off.p, r0, n,
                                                    (uint32_t)ctx->n_cigar, ctx->n_qual);
     ctx->launches += 2;
-    if (r0 == 0) ctx->long_mode = b->n_cigar > 4 * b->n_reads;     // decided once per contig
+    // Long-read mode (read ends + CIGAR checkpoints, every window on the general kernel) starts with the first batch that
+    // looks like long reads -- normally the first batch of the contig; if it is a later one, the reads already resident are
+    // checkpointed too (windows launched before the switch stay valid: results do not depend on which kernel took a window).
+    uint32_t ck_from = r0;
+    if (!ctx->long_mode && b->n_cigar > 4 * b->n_reads) { ctx->long_mode = true; ck_from = 0; }
     if (ctx->long_mode) {
         // read ends, maximum span and CIGAR checkpoints in one pass (one warp per read)
         if ((rc = ensure(ctx, ctx->read_end, ((size_t)r0 + n + 1) * 4, true, ctx->s_compute))) return rc;
         if ((rc = ensure(ctx, ctx->cigar_ckpt, ((ctx->n_cigar + b->n_cigar) / 32 + 2) * sizeof(uint2), true, ctx->s_compute))) return rc;
-        k_cigar_checkpoints<<<(n + 7) / 8, 256, 0, ctx->s_compute>>>((const int32_t *)ctx->pos.p, (const uint32_t *)ctx->cigar_off.p,
-                                                                     (const uint32_t *)ctx->cigar.p, r0, r0 + n, (uint32_t *)ctx->read_end.p,
+        k_cigar_checkpoints<<<(r0 + n - ck_from + 7) / 8, 256, 0, ctx->s_compute>>>((const int32_t *)ctx->pos.p, (const uint32_t *)ctx->cigar_off.p,
+                                                                     (const uint32_t *)ctx->cigar.p, ck_from, r0 + n, (uint32_t *)ctx->read_end.p,
                                                                      ctx->span_on_device ? (uint32_t *)ctx->misc.p + M_MAXSPAN : nullptr,
                                                                      (uint2 *)ctx->cigar_ckpt.p);
         ctx->launches++;

@@ -371,3 +371,21 @@ def test_byte_wide_thresholds_on_a_deep_short_read_pile(min_depth, max_depth, mi
                           max_low_mapq=3)
     o, results = assert_parity([(c.name, 0, c.length, c.ref, c.reads)], opt)
     assert results[0].general_windows < 5          # the pile stays below 255: the fast kernel takes (nearly) all windows
+
+
+def test_long_reads_arriving_after_short_read_batches(ctx_default):
+    """A contig whose first batches are short reads and whose later batches are indel-heavy long reads: long-read mode
+    (checkpoints, general kernel) switches on at the first long batch and the result is the oracle's either way."""
+    a = synth.synth_short("chr5", 120_000, seed=21)
+    b = synth.synth_long("chr5", 120_000, seed=22, depth=8.0)
+    first = a.reads.select(a.reads.pos < 60_000)
+    later = b.reads.select(b.reads.pos >= 60_000)
+    reads = ReadColumns(np.concatenate([first.pos, later.pos]), np.concatenate([first.flag, later.flag]),
+                        np.concatenate([first.mapq, later.mapq]),
+                        np.concatenate([first.cigar_off, later.cigar_off[1:] + first.cigar_off[-1]]).astype(np.uint32),
+                        np.concatenate([first.cigar, later.cigar]),
+                        np.concatenate([first.qual_off, later.qual_off[1:] + first.qual_off[-1]]).astype(np.uint64),
+                        np.concatenate([first.qual, later.qual]), np.arange(first.n + later.n, dtype=np.uint32))
+    assert np.all(np.diff(reads.pos.astype(np.int64)) >= 0)
+    for batch_reads in (0, first.n, 5000):
+        assert_parity([("chr5", 0, a.length, a.ref, reads)], CallableOptions(), ctx_default, batch_reads=batch_reads)
