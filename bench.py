@@ -310,9 +310,10 @@ class Nccl:
             pass
 
 
-def kernel_config_run(tag, c, opt, peak):
-    """One reduced-scale BASELINE config: admission, upload, then the HBM-resident kernel time (best of 4 re-runs)."""
-    from decodingustools_b200.callable_loci import CallableLociContext, admit_reads, compact_reads
+def kernel_config_run(tag, c, opt, peak, check=True):
+    """One reduced-scale BASELINE config: admission, upload, then the HBM-resident kernel time (best of 4 re-runs); the
+    result (BED text, counters, bins) is compared with the CPU oracle run on the same offered records."""
+    from decodingustools_b200.callable_loci import CallableLociContext, CallableProfiler, admit_reads, compact_reads
     t0 = time.perf_counter()
     st = {}
     keep = admit_reads(c.reads, opt.pileup_max_depth, 0, threads=0, stats=st)
@@ -321,13 +322,23 @@ def kernel_config_run(tag, c, opt, peak):
     ctx = CallableLociContext(opt)
     ctx.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
     ctx.push_reads(reads)
-    r = ctx.finish_contig(copy_intervals=False)
+    r = ctx.finish_contig(copy_intervals=check)
+    parity = None
+    if check:
+        prof = CallableProfiler(None, c.length)
+        prof.add_contig(c.name, c.length, r.intervals, r.state_counts, r.bins.copy(), r.stride)
+        gbed = prof.bed_bytes()
     runs = [ctx.rerun_resident(fetch=True) for _ in range(4)]
     best = min(runs, key=lambda x: x[1].pileup_ms)
     step_ms, res = best
     byts = reads.nbytes_device() + c.length // 8
     ctx.close()
-    return {"config": tag, "contig_bp": c.length, "reads_offered": c.reads.n, "reads_admitted": reads.n, "cigar_ops": reads.n_cigar,
+    if check:
+        oc, orun, dt, _ = oracle_run(c, c.reads, opt, c.length)
+        parity = bool(orun.bed() == gbed and r.state_counts.tolist() == oc.counts and r.n_covered_bases == oc.n_covered_bases
+                      and r.summed_coverage == oc.summed_coverage and r.summed_baseq == oc.summed_baseq and r.summed_mapq == oc.summed_mapq
+                      and r.quality_bases == oc.quality_bases and oc.bins is not None and np.array_equal(r.bins, oc.bins))
+    return {"config": tag, "parity": parity, "contig_bp": c.length, "reads_offered": c.reads.n, "reads_admitted": reads.n, "cigar_ops": reads.n_cigar,
             "cells": int(r.summed_coverage), "pileup_ms": round(res.pileup_ms, 4), "step_ms": round(step_ms, 4),
             "upload_kernels_ms": round(r.upload_ms, 4), "general_windows": int(res.general_windows),
             "Gbases_s": round(r.summed_coverage / res.pileup_ms / 1e6, 1), "frac": round(byts / res.pileup_ms / 1e6 / peak, 4),

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from decodingustools_b200 import synth
-from decodingustools_b200.callable_loci import (CallableLociContext, admit_reads, stitch_intervals)
+from decodingustools_b200.callable_loci import (CallableLociContext, admit_reads, compact_reads, stitch_intervals)
 from decodingustools_b200.options import CallableOptions
 from decodingustools_b200.soa import ReadColumns
 from tests.helpers import assert_parity, run_oracle
@@ -389,3 +389,16 @@ def test_long_reads_arriving_after_short_read_batches(ctx_default):
     assert np.all(np.diff(reads.pos.astype(np.int64)) >= 0)
     for batch_reads in (0, first.n, 5000):
         assert_parity([("chr5", 0, a.length, a.ref, reads)], CallableOptions(), ctx_default, batch_reads=batch_reads)
+
+
+def test_queued_reruns_leave_the_same_result(ctx_default):
+    """clb_rerun_resident(ctx, NULL, NULL) only enqueues: three steps queued back to back, waited for once."""
+    c = synth.synth_short("chr22", 400_000, seed=31)
+    ctx_default.begin_contig(0, c.name, c.length, c.ref, c.length, max_ref_span=c.reads.max_ref_span())
+    ctx_default.push_reads(compact_reads(c.reads, admit_reads(c.reads, 500)))
+    first = ctx_default.finish_contig()
+    for _ in range(3):
+        assert ctx_default.rerun_resident(fetch=False, sync=False) == (None, None)
+    again = ctx_default.refresh_counters()
+    assert np.array_equal(again.intervals, first.intervals) and np.array_equal(again.state_counts, first.state_counts)
+    assert np.array_equal(again.bins, first.bins) and again.summed_baseq == first.summed_baseq and again.summed_mapq == first.summed_mapq
