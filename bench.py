@@ -560,8 +560,15 @@ def main():
         allreduce_ok = bool(np.array_equal(summed.state_counts, first.state_counts * np.uint64(world))
                             and summed.summed_coverage == world * first.summed_coverage and summed.summed_baseq == world * first.summed_baseq
                             and np.array_equal(summed.bins.astype(np.uint64), first.bins.astype(np.uint64) * np.uint64(world)))
-    _, res = ctx.rerun_resident(fetch=True)
+    _, res = ctx.rerun_resident(fetch=True, copy_intervals=True)
     pileup_ms, fast_ms, general_windows = res.pileup_ms, res.fast_ms, res.general_windows
+    # what the resident steps compute is what the e2e pass (checked against the oracle below) computed
+    resident_ok = bool(np.array_equal(res.intervals, first.intervals) and np.array_equal(res.state_counts, first.state_counts)
+                       and np.array_equal(res.bins, first.bins) and res.summed_coverage == first.summed_coverage
+                       and res.summed_baseq == first.summed_baseq and res.summed_mapq == first.summed_mapq
+                       and res.quality_bases == first.quality_bases and res.n_covered_bases == first.n_covered_bases)
+    if not resident_ok:
+        raise SystemExit("the HBM-resident step does not reproduce the result of the e2e pass")
     launches_per_step = res.gpu_launches
 
     # ---------------- end-to-end leg through the public API with host buffers (admission and BED text inside)
@@ -721,6 +728,7 @@ def main():
                     "bed_bytes": os.path.getsize(bed_path),
                     "note": "per contig: clb_admit_reads_mt (htslib depth cap) + clb_begin_contig + clb_push_reads batches from page-locked host "
                             "columns + clb_finish_contig (D2H) + clb_bed_writer_* to a real file; the device part is PCIe-bound"},
+            "resident_equals_e2e": resident_ok,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "kernel_step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
