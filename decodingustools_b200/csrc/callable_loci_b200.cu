@@ -75,7 +75,7 @@ struct clb_ctx {
 
 // misc layout (uint32): record cursor, error bits, n_total intervals, deep-window count, general-queue count / tickets taken
 // (these six are reset per run), then the maximum reference span
-enum { M_CURSOR = 0, M_ERR = 1, M_NTOTAL = 2, M_DEEP = 3, M_GEN_COUNT = 4, M_GEN_TAKEN = 5, M_RESET_WORDS = 6, M_MAXSPAN = 7, M_WORDS = 8 };
+enum { M_CURSOR = 0, M_ERR = 1, M_NTOTAL = 2, M_DEEP = 3, M_GEN_COUNT = 4, M_GEN_TAKEN = 5, M_RESET_WORDS = 6, M_MAXSPAN = 7, M_MAXQLEN = 8, M_WORDS = 9 };
 
 namespace {
 
@@ -164,10 +164,11 @@ int launch_windows(clb_ctx *ctx, uint32_t w0, uint32_t w1, EvPair *time_pileup =
     if (w1 <= w0) return CLB_OK;
     const uint32_t n = w1 - w0;
     const bool all_general = ctx->force_general || ctx->long_mode;
-    k_window_ranges<<<(n + 7) / 8, 256, 0, ctx->s_compute>>>(                    // one warp per window
+    k_window_ranges<<<(unsigned)(((uint64_t)n * WR_LANES + 255) / 256), 256, 0, ctx->s_compute>>>(   // WR_LANES lanes per window
         (const int32_t *)ctx->pos.p, (uint32_t)ctx->n_reads, ctx->region_start, ctx->region_end,
         (const uint32_t *)ctx->misc.p + M_MAXSPAN, w0, n, (const uint64_t *)ctx->qual_off.p, (const uint32_t *)ctx->cigar_off.p, ctx->stride,
-        (uint4 *)ctx->win_rec.p, all_general ? 1u : 0u, (uint32_t *)ctx->gen_list.p, (uint32_t *)ctx->misc.p + M_GEN_COUNT);
+        (uint4 *)ctx->win_rec.p, all_general ? 1u : 0u, (uint32_t *)ctx->gen_list.p, (uint32_t *)ctx->misc.p + M_GEN_COUNT,
+        (const uint32_t *)ctx->misc.p + M_MAXQLEN);
     KParams P = make_params(ctx);
     P.win_first = w0;
     if (time_pileup) CU(cudaEventRecord(time_pileup->a, ctx->s_compute));
@@ -485,6 +486,7 @@ int clb_begin_contig(clb_ctx *ctx, int32_t tid, const char *name, uint32_t conti
     if ((rc = alloc_outputs(ctx))) return rc;
     if ((rc = reset_accumulators(ctx))) return rc;
     CU(cudaMemcpyAsync((uint32_t *)ctx->misc.p + M_MAXSPAN, &max_ref_span, 4, cudaMemcpyHostToDevice, ctx->s_compute));
+    CU(cudaMemsetAsync((uint32_t *)ctx->misc.p + M_MAXQLEN, 0, 4, ctx->s_compute));
     // offsets column entry 0
     if ((rc = ensure(ctx, ctx->cigar_off, 4096, false, ctx->s_compute))) return rc;
     if ((rc = ensure(ctx, ctx->qual_off, 4096, false, ctx->s_compute))) return rc;
@@ -548,7 +550,8 @@ int clb_push_reads(clb_ctx *ctx, const clb_read_batch *b) {
     CU(cudaEventRecord(eu.a, ctx->s_compute));
     const uint32_t nb = (n + 255) / 256;
     k_validate_batch<<<nb, 256, 0, ctx->s_compute>>>((const int32_t *)ctx->pos.p, (const uint32_t *)ctx->cigar_off.p,
-                                                     (const uint64_t *)ctx->qual_off.p, r0, n, (uint32_t *)ctx->misc.p + M_ERR);
+                                                     (const uint64_t *)ctx->qual_off.p, r0, n, (uint32_t *)ctx->misc.p + M_ERR,
+                                                     (uint32_t *)ctx->misc.p + M_MAXQLEN);
     k_rebase_batch<<<nb, 256, 0, ctx->s_compute>>>((uint32_t *)ctx->cigar_off.p, (uint64_t *)ctx->qual_off.p, r0, n,
                                                    (uint32_t)ctx->n_cigar, ctx->n_qual);
     ctx->launches += 2;

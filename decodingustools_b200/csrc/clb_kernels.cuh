@@ -943,40 +943,51 @@ __global__ void __launch_bounds__(NT, 1) k_pileup_classify_deep(const KParams P)
 // ---------------------------------------------------------------------------------------------
 // Small helper kernels
 // ---------------------------------------------------------------------------------------------
-// Warp-cooperative lower bound: 32 probes per round trip (the range shrinks 33-fold per step: 6 dependent loads for 48 M
-// reads instead of 26).
-__device__ __forceinline__ uint32_t lower_bound_pos_warp(const int32_t *pos, uint32_t n, long long key, int lane) {
+#ifndef CLB_WR_LANES
+#define CLB_WR_LANES 8
+#endif
+constexpr int WR_LANES = CLB_WR_LANES;   // lanes that share one window in k_window_ranges (a power of two <= 32)
+static_assert(WR_LANES >= 2 && WR_LANES <= 32 && (WR_LANES & (WR_LANES - 1)) == 0, "lane group");
+
+// Lower bound by a group of GS lanes: GS probes per round trip (the range shrinks (GS + 1)-fold per step).  gmask = the
+// group's lanes, gl = lane within the group, gbase = first lane of the group.
+__device__ __forceinline__ uint32_t lower_bound_pos_group(const int32_t *pos, uint32_t n, long long key, uint32_t gmask, int gl, int gbase) {
+    constexpr uint32_t GS = WR_LANES;
     uint32_t lo = 0, hi = n;                             // the answer lies in [lo, hi]
-    while (hi - lo > 32u) {
-        const uint32_t idx = lo + (uint32_t)(((unsigned long long)(hi - lo) * (unsigned)(lane + 1)) / 33u);   // lo < idx < hi, increasing with the lane
-        const uint32_t below = __ballot_sync(FULL, (long long)pos[idx] < key);                                // monotone: a run of ones, then zeros
+    while (hi - lo > GS) {
+        const uint32_t idx = lo + (uint32_t)(((unsigned long long)(hi - lo) * (unsigned)(gl + 1)) / (GS + 1u));   // lo < idx < hi, increasing with the lane
+        const uint32_t below = (__ballot_sync(gmask, (long long)pos[idx] < key) >> gbase) & (GS == 32u ? 0xffffffffu : ((1u << GS) - 1u));   // a run of ones, then zeros
         const int c = __popc(below);
-        const uint32_t lo_n = c ? __shfl_sync(FULL, idx, c - 1) + 1u : lo;
-        const uint32_t hi_n = c < 32 ? __shfl_sync(FULL, idx, c & 31) : hi;
-        lo = lo_n; hi = hi_n;
+        const uint32_t lo_n = __shfl_sync(gmask, idx, gbase + max(c - 1, 0)) + 1u;
+        const uint32_t hi_n = __shfl_sync(gmask, idx, gbase + min(c, (int)GS - 1));
+        lo = c ? lo_n : lo; hi = c < (int)GS ? hi_n : hi;
     }
-    const uint32_t i = lo + (uint32_t)lane;
-    return lo + (uint32_t)__popc(__ballot_sync(FULL, i < hi && (long long)pos[i] < key));
+    const uint32_t i = lo + (uint32_t)gl;
+    return lo + (uint32_t)__popc(__ballot_sync(gmask, i < hi && (long long)pos[i] < key) & gmask);
 }
 
 // candidate read range of every window: reads with pos < window end and pos + max_span > halo position; and the
 // window's class: shard-first windows (they need the state of the base before the shard), windows of long-read contigs
 // and windows whose candidate count or CIGAR density cannot be an ordinary short-read pile go straight to the general queue.
-// One warp per window: the searches probe 32 positions per step and the two verification loops are spread over the lanes
-// (one thread per window spent 80 us of a 2.8 ms chr1 step in ~70 dependent round trips).
+// A group of WR_LANES lanes per window: the searches probe WR_LANES positions per step and the two verification loops are
+// spread over the group.  The kernel is bound by (dependent round trips per window) x (waves of warps): one thread per
+// window spent 82 us of a chr1 step in ~70 round trips, a whole warp per window 12 round trips but 13 waves of warps.
 __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t region_start, uint32_t region_end,
                                 const uint32_t *max_span_ptr, uint32_t w_first, uint32_t n_w,
                                 const uint64_t *qual_off, const uint32_t *cigar_off, uint32_t stride, uint4 *win_rec,
-                                uint32_t force_general, uint32_t *gen_list, uint32_t *gen_count) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= n_w) return;                                // whole warps leave together
+                                uint32_t force_general, uint32_t *gen_list, uint32_t *gen_count, const uint32_t *max_qlen_ptr) {
+    constexpr uint32_t GS = WR_LANES;
+    const uint32_t gi = (blockIdx.x * blockDim.x + threadIdx.x) / GS;     // window of this group (groups past the end run a clamped copy: whole warps stay converged)
+    const int lane = threadIdx.x & 31, gl = lane & (int)(GS - 1u), gbase = lane - gl;
+    const uint32_t gmask = (GS == 32u ? 0xffffffffu : ((1u << GS) - 1u)) << gbase;
+    const bool real = gi < n_w;
+    const uint32_t i = real ? gi : n_w - 1u;
     const uint32_t max_span = *max_span_ptr;
     const uint32_t w = w_first + i;
     const long long wb = (long long)region_start + (long long)w * WREAL - 1;
     const long long wend = min(wb + WN, (long long)region_end);
-    const uint32_t r_lo = lower_bound_pos_warp(pos, n_reads, wb - (long long)max_span + 1, lane);
-    const uint32_t r_hi = lower_bound_pos_warp(pos, n_reads, wend, lane);
+    const uint32_t r_lo = lower_bound_pos_group(pos, n_reads, wb - (long long)max_span + 1, gmask, gl, gbase);
+    const uint32_t r_hi = lower_bound_pos_group(pos, n_reads, wend, gmask, gl, gbase);
     const uint32_t first_bin = stride ? (uint32_t)(wb + 1) / stride : 0u;
     const uint64_t q_lo = qual_off[r_lo] & ~15ull, q_hi = qual_off[r_hi];
     const uint32_t n_cand = r_hi - r_lo;
@@ -987,9 +998,9 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     // at the first sample and goes to the general kernel without a wasted attempt
     if (!general) {
         bool deep = false;
-        for (uint32_t i2 = r_lo + 254u * (uint32_t)(lane + 1); i2 < r_hi; i2 += 254u * 32u)
+        for (uint32_t i2 = r_lo + 254u * (uint32_t)(gl + 1); i2 < r_hi; i2 += 254u * GS)
             deep |= (long long)pos[i2 - 254u] + (long long)max_span > (long long)pos[i2];
-        general = __any_sync(FULL, deep);
+        general = (__ballot_sync(gmask, deep) & gmask) != 0u;
     }
     // Sub-batches of the fast kernel: G <= 32 reads at a time (one per lane) whose qualities fit a warp's stage.  Start
     // from the mean read length of the window and verify every sub-batch; shrink a few times before giving up.
@@ -997,19 +1008,22 @@ __global__ void k_window_ranges(const int32_t *pos, uint32_t n_reads, uint32_t r
     if (!general && n_cand) {
         const uint64_t total = q_hi - q_lo;
         if (total * 32u > (uint64_t)(CLB_F_WSTAGE - 16) * n_cand) G = (uint32_t)(((uint64_t)(CLB_F_WSTAGE - 16) * n_cand) / total);
-        bool ok = false;
+        // no sub-batch of G reads can outgrow the stage when even G reads of the contig's longest quality string fit (k_validate_batch
+        // tracks that maximum): uniform-length reads skip the verification, which touches qual_off once per sub-batch
+        const uint32_t max_qlen = *max_qlen_ptr;
+        bool ok = G >= 4u && max_qlen != 0u && (uint64_t)G * max_qlen + 32u <= (uint64_t)CLB_F_WSTAGE;
         for (int tries = 0; tries < 4 && G >= 4u && !ok; tries++) {
             uint32_t worst = 0;                          // staged bytes of the largest sub-batch, saturated
-            for (uint32_t b = r_lo + (uint32_t)lane * G; b < r_hi; b += 32u * G) {
+            for (uint32_t b = r_lo + (uint32_t)gl * G; b < r_hi; b += GS * G) {
                 const uint64_t bytes = (qual_off[min(b + G, r_hi)] - (qual_off[b] & ~15ull) + 15ull) & ~15ull;
                 worst = max(worst, (uint32_t)min(bytes, (uint64_t)0xffffffffu));
             }
-            ok = __reduce_max_sync(FULL, worst) <= (uint32_t)CLB_F_WSTAGE;
+            ok = __reduce_max_sync(gmask, worst) <= (uint32_t)CLB_F_WSTAGE;
             if (!ok) G -= max(1u, G / 8u);
         }
         if (!ok) general = true;
     }
-    if (lane == 0) {
+    if (real && gl == 0) {
         win_rec[3 * (size_t)w] = make_uint4(r_lo, r_hi, first_bin, stride ? (uint32_t)((long long)(first_bin + 1) * stride - wb) : 0xffffffffu);
         *reinterpret_cast<ulonglong2 *>(win_rec + 3 * (size_t)w + 1) = make_ulonglong2(q_lo, q_hi);
         win_rec[3 * (size_t)w + 2] = make_uint4(general ? 0u : G, general ? 0u : (n_cand + G - 1u) / G, c_lo, c_hi);   // reads per sub-batch, sub-batches, CIGAR op range
@@ -1054,13 +1068,20 @@ __global__ void k_cigar_checkpoints(const int32_t *pos, const uint32_t *cigar_of
 // batch append, step 1: validate ordering of the freshly copied (still batch-relative) columns.
 // Device entries r0+1 .. r0+n hold the batch's offsets[1..n]; entry r0 is the previous batch's end.
 __global__ void k_validate_batch(const int32_t *pos, const uint32_t *cigar_off, const uint64_t *qual_off, uint32_t r0, uint32_t n,
-                                 uint32_t *err) {
+                                 uint32_t *err, uint32_t *max_qlen) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (pos[r0 + i] < 0 || (r0 + i > 0 && pos[r0 + i] < pos[r0 + i - 1])) atomicOr(err, ERR_UNSORTED);
-    const uint32_t cprev = i == 0 ? 0u : cigar_off[r0 + i];
-    const uint64_t qprev = i == 0 ? 0ull : qual_off[r0 + i];
-    if (cigar_off[r0 + i + 1] < cprev || qual_off[r0 + i + 1] < qprev) atomicOr(err, ERR_OFFSETS);
+    uint32_t ql = 0;
+    if (i < n) {
+        if (pos[r0 + i] < 0 || (r0 + i > 0 && pos[r0 + i] < pos[r0 + i - 1])) atomicOr(err, ERR_UNSORTED);
+        const uint32_t cprev = i == 0 ? 0u : cigar_off[r0 + i];
+        const uint64_t qprev = i == 0 ? 0ull : qual_off[r0 + i];
+        const uint64_t qnext = qual_off[r0 + i + 1];
+        if (cigar_off[r0 + i + 1] < cprev || qnext < qprev) atomicOr(err, ERR_OFFSETS);
+        ql = qnext >= qprev ? (uint32_t)min(qnext - qprev, (uint64_t)0xffffffffu) : 0xffffffffu;
+    }
+    // longest quality string of the contig (saturated): k_window_ranges sizes the fast kernel's sub-batches with it
+    const uint32_t wmax = __reduce_max_sync(FULL, ql);               // every lane of the warp is here
+    if ((threadIdx.x & 31) == 0 && wmax) atomicMax(max_qlen, wmax);
 }
 // step 2: rebase entries r0+1 .. r0+n onto the contig-wide payload arrays
 __global__ void k_rebase_batch(uint32_t *cigar_off, uint64_t *qual_off, uint32_t r0, uint32_t n, uint32_t cigar_base, uint64_t qual_base) {
