@@ -6,9 +6,11 @@
 // round-1 kernel, so results never depend on which kernel took a window.
 //
 // What is different from the general kernel, and why (ncu of round 1: issue bound at 0.416 warp instructions per cell):
-//   * The qualities of 256 consecutive reads are ONE contiguous byte range: one elected thread moves it into shared
-//     memory with a single cp.async.bulk (TMA engine, completion on an mbarrier that doubles as the CTA barrier
-//     behind the CIGAR phase).  No per-thread address math, no LDG wavefronts, no descriptor pool.
+//   * Every warp runs its own pipeline over sub-batches of <= 32 consecutive reads (one per lane).  The qualities of a
+//     sub-batch are ONE contiguous byte range: lane 0 moves it into the warp's stage with a single cp.async.bulk (TMA
+//     engine, completion on the warp's own mbarrier) and the CIGAR walk of the 32 reads runs while the copy is in
+//     flight.  No per-thread address math for the qualities, no LDG wavefronts, no descriptor pool, no CTA barrier
+//     until phase C.
 //   * Every thread then streams ITS OWN read's M-segment from shared memory with LDS.128: the segment lives in
 //     registers, interior chunks need no byte masks, the loop is 6 instructions per 4 bases.
 //   * Base-quality PASS counts go to four packed-u8 arrays selected by (entry of chunk byte 0) mod 4, so the four
