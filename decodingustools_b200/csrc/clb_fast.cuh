@@ -27,7 +27,7 @@ namespace clb {
 
 constexpr int F_CW = 520;                 // words per alignment-class array (2048 / 4 + 8; 520 % 32 == 8 staggers the banks)
 constexpr int F_WSTAGE = CLB_F_WSTAGE;    // staged quality bytes per warp and sub-batch of <= 32 reads (k_window_ranges sizes the sub-batches)
-constexpr int F_XCAP = 128;               // second-and-later M-segments per window (streamed from global memory at the end)
+constexpr int F_XCAP = 96;                // second-and-later M-segments per window (streamed from global memory at the end; more: general kernel)
 constexpr int F_MAXOPS = 64;              // longest CIGAR walked lane-serially
 constexpr int F_LOOKBACK = 254;           // depth proof: pos[i] - pos[i - 254] >= max span  =>  depth <= 254 everywhere
 constexpr int F_NFIRST = 256;             // low-MAPQ threshold table entries, one byte each (raw depth <= 254)

@@ -413,7 +413,7 @@ __device__ __forceinline__ uint32_t first_low(uint32_t raw, double fraction) {
 }
 
 #ifndef CLB_F_WSTAGE
-#define CLB_F_WSTAGE 4848                 // quality bytes one warp of k_pileup_fast stages per sub-batch of <= 32 reads (clb_fast.cuh)
+#define CLB_F_WSTAGE 4880                 // quality bytes one warp of k_pileup_fast stages per sub-batch of <= 32 reads (clb_fast.cuh): 32 x 151 + alignment slack
 #endif
 #ifndef CLB_PREFETCH_MAX
 #define CLB_PREFETCH_MAX (128u << 10)     // bytes of a window's qualities prefetched into L2 at window start

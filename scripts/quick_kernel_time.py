@@ -11,7 +11,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 mode = sys.argv[3] if len(sys.argv) > 3 else "short"
 opt = CallableOptions()
 L = int(synth.HG38["chr1"] * scale)
-c = synth.synth_short("chr1", L, 1) if mode == "short" else synth.synth_long("chr1", L, 1)
+c = synth.synth_short("chr1", L, 1, read_len=int(os.environ.get("CLB_READ_LEN", "150"))) if mode == "short" else synth.synth_long("chr1", L, 1)
 reads = compact_reads(c.reads, admit_reads(c.reads, 500, 0))
 ctx = CallableLociContext(opt)
 ctx.begin_contig(0, "chr1", c.length, c.ref, c.length, max_ref_span=reads.max_ref_span())
