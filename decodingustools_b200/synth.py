@@ -161,10 +161,18 @@ def synth_short(name: str, length: int, seed: int, depth: float = 30.0, read_len
     kind[u < 0.045] = 3
     kind[u < 0.03] = 2
     kind[u < 0.015] = 1
-    k = rng.integers(1, 51, size=n)                      # clip length
-    ins = rng.integers(1, 11, size=n)
+    if read_len >= 71:                                   # (the draws of the standard read lengths must not change: seeded workloads)
+        k_hi, ins_hi, a_lo, a_hi = 51, 11, 10, read_len - 20
+    else:                                                # short reads: clips and indels scaled so that every op keeps a positive length
+        if read_len < 12:
+            raise ValueError("synth_short needs read_len >= 12")
+        k_hi, ins_hi = read_len // 3 + 1, read_len // 6 + 1
+        a_lo = read_len // 4
+        a_hi = max(a_lo + 1, read_len - read_len // 4 - ins_hi)
+    k = rng.integers(1, k_hi, size=n)                    # clip length
+    ins = rng.integers(1, ins_hi, size=n)
     dele = rng.integers(1, 31, size=n)
-    a = rng.integers(10, read_len - 20, size=n)          # left M length for indel reads
+    a = rng.integers(a_lo, a_hi, size=n)                 # left M length for indel reads
     nops = np.ones(n, dtype=np.int64)
     nops[(kind == 1) | (kind == 2)] = 2
     nops[(kind == 3) | (kind == 4)] = 3
@@ -192,6 +200,7 @@ def synth_short(name: str, length: int, seed: int, depth: float = 30.0, read_len
     qlen[no_seq] = 0
     qual_off = np.concatenate([[0], np.cumsum(qlen)]).astype(np.uint64)
     qual = _fill_quals(int(qual_off[-1]), rng, qual_device)
+    assert int((cigar >> 4).max(initial=1)) <= read_len + 30 and int((cigar >> 4).min(initial=1)) >= 1, "generator produced an empty or wrapped CIGAR op"
     reads = ReadColumns(pos.astype(np.int32), flag, mapq, cigar_off.astype(np.uint32), cigar, qual_off, qual, name_id)
     return SynthContig(name, length, ref, reads, blocks)
 
