@@ -74,3 +74,18 @@ def test_random_multi_contig_with_quirks(seed):
     o, n = run_both(contigs, CallableOptions(min_depth=2, max_depth=4))
     order, fl, sm = o.export()
     assert sm["total_bases"] == sum(c[2] for c in contigs)
+
+
+@pytest.mark.parametrize("read_len", [12, 36, 70, 71, 151, 250])
+def test_synthetic_generator_keeps_every_cigar_op_positive(read_len):
+    """synth_short for other read lengths than 150: every op has a positive length, the query lengths match the quality
+    strings, reads stay inside the contig (an earlier version wrapped op lengths to 2^28 for reads shorter than 71 bases)."""
+    from decodingustools_b200 import synth
+    from decodingustools_b200.soa import CONSUMES_QUERY
+    c = synth.synth_short("chrS", 40_000, seed=7, depth=20.0, read_len=read_len)
+    r = c.reads
+    assert r.n > 0 and int((r.cigar >> 4).min()) >= 1 and int((r.cigar >> 4).max()) <= read_len + 30
+    qlen = np.add.reduceat(((r.cigar >> 4) * CONSUMES_QUERY[r.cigar & 15]).astype(np.int64), r.cigar_off[:-1].astype(np.int64))
+    have = np.diff(r.qual_off.astype(np.int64))
+    assert np.all((have == qlen) | (have == 0))                           # SEQ '*' records carry no qualities
+    assert int(r.end().max()) <= c.length and np.all(np.diff(r.pos.astype(np.int64)) >= 0)
